@@ -1,0 +1,232 @@
+"""ctypes binding of libapde.so (C-ABI declared in include/apde.h).
+
+The library is the only compute path: if it is missing, or no sm_100 GPU is usable, every solve
+raises.  Nothing here imports the CPU oracle.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+LIB_PATH = os.environ.get("APDE_LIBRARY", os.path.join(_ROOT, "lib", "libapde.so"))
+
+_dp = ctypes.POINTER(ctypes.c_double)
+_i64 = ctypes.c_int64
+_i64p = ctypes.POINTER(ctypes.c_int64)
+_vp = ctypes.c_void_p
+
+APDE_OK = 0
+ERROR_NAMES = {-1: "APDE_EINVAL", -2: "APDE_ENODEV", -3: "APDE_ECUDA", -4: "APDE_ENOMEM", -5: "APDE_ESTATE"}
+
+# every symbol include/apde.h declares (tests check that the shared object exports each one)
+EXPORTED_SYMBOLS = (
+    "apde_version", "apde_device_count", "apde_last_error",
+    "apde_solve_exact_f64", "apde_solve_exact_f64_path", "apde_solve_redblack_f64", "apde_solve_redblack_f32",
+    "apde_plan_create", "apde_plan_destroy", "apde_plan_upload", "apde_plan_fill",
+    "apde_plan_download", "apde_plan_run", "apde_plan_halo", "apde_plan_residuals",
+    "apde_plan_read_residuals", "apde_plan_launch_count", "apde_plan_checksum", "apde_memcpy_dtod",
+)
+
+
+class ApdeError(RuntimeError):
+    """A libapde call failed; carries the C error code."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"{ERROR_NAMES.get(code, code)}: {message}")
+        self.code = code
+
+
+class PlanDesc(ctypes.Structure):
+    _fields_ = [("dtype_bytes", ctypes.c_int32), ("has_noise", ctypes.c_int32),
+                ("has_source", ctypes.c_int32), ("temporal_depth", ctypes.c_int32),
+                ("grows", _i64), ("cols", _i64), ("row_begin", _i64), ("row_end", _i64)]
+
+
+class FillDesc(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("top_hot", ctypes.c_int32),
+                ("noise_level", ctypes.c_double), ("seed", ctypes.c_uint64)]
+
+
+_lib = None
+
+
+def load():
+    """Load libapde.so once.  Raises (never falls back) when the library is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  analog_pde_solver has no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.apde_version.restype = ctypes.c_int
+    lib.apde_device_count.restype = ctypes.c_int
+    lib.apde_last_error.restype = ctypes.c_char_p
+    solve_tail = [_i64, _i64, ctypes.c_double, _i64]
+    lib.apde_solve_exact_f64.restype = ctypes.c_int
+    lib.apde_solve_exact_f64.argtypes = [_dp, _dp, _dp, _dp] + solve_tail + [_dp, _i64p, _dp]
+    lib.apde_solve_exact_f64_path.restype = ctypes.c_int
+    lib.apde_solve_exact_f64_path.argtypes = [_dp, _dp, _dp, _dp] + solve_tail + [_dp, _i64p, _dp, ctypes.c_int]
+    for name in ("apde_solve_redblack_f64", "apde_solve_redblack_f32"):
+        fn = getattr(lib, name)
+        fn.restype = ctypes.c_int
+        fn.argtypes = [_dp, _dp, _dp, _dp] + solve_tail + [ctypes.c_int, ctypes.c_int, _dp, _i64p, _dp]
+    lib.apde_plan_create.restype = ctypes.c_int
+    lib.apde_plan_create.argtypes = [ctypes.POINTER(_vp), ctypes.POINTER(PlanDesc)]
+    lib.apde_plan_destroy.restype = ctypes.c_int
+    lib.apde_plan_destroy.argtypes = [_vp]
+    lib.apde_plan_upload.restype = ctypes.c_int
+    lib.apde_plan_upload.argtypes = [_vp, _dp, _dp, _dp, _dp]
+    lib.apde_plan_fill.restype = ctypes.c_int
+    lib.apde_plan_fill.argtypes = [_vp, ctypes.POINTER(FillDesc)]
+    lib.apde_plan_download.restype = ctypes.c_int
+    lib.apde_plan_download.argtypes = [_vp, _dp]
+    lib.apde_plan_run.restype = ctypes.c_int
+    lib.apde_plan_run.argtypes = [_vp, _i64, _i64, ctypes.c_int, _vp]
+    lib.apde_plan_halo.restype = ctypes.c_int
+    lib.apde_plan_halo.argtypes = [_vp, ctypes.c_int, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i64p]
+    lib.apde_plan_residuals.restype = ctypes.c_int
+    lib.apde_plan_residuals.argtypes = [_vp, ctypes.POINTER(_vp), _i64p]
+    lib.apde_plan_read_residuals.restype = ctypes.c_int
+    lib.apde_plan_read_residuals.argtypes = [_vp, _i64, _i64, _dp, _vp]
+    lib.apde_plan_launch_count.restype = _i64
+    lib.apde_plan_launch_count.argtypes = [_vp]
+    lib.apde_plan_checksum.restype = ctypes.c_int
+    lib.apde_plan_checksum.argtypes = [_vp, _dp, _dp, _vp]
+    lib.apde_memcpy_dtod.restype = ctypes.c_int
+    lib.apde_memcpy_dtod.argtypes = [_vp, _vp, _i64, _vp]
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != APDE_OK:
+        msg = load().apde_last_error()
+        raise ApdeError(rc, msg.decode("utf-8", "replace") if msg else "unknown error")
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return ctypes.cast(None, _dp) if a is None else a.ctypes.data_as(_dp)
+
+
+def _as_f64(a, shape, name):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if a.shape != tuple(shape):
+        raise ValueError(f"{name}: expected shape {tuple(shape)}, got {a.shape}")
+    return a
+
+
+EXACT_PATHS = {"auto": 0, "small": 1, "ring": 2}
+
+
+def solve(mode: str, grid: np.ndarray, noise_h, noise_v, source, tol: float, max_iter: int,
+          check_every: int = 0, temporal_depth: int = 0, exact_path: str = "auto"):
+    """One relaxation solve on the GPU.  `grid` (float64, C-order) is updated in place.
+
+    mode: "exact" (bit-exact wavefront, fp64), "redblack" (fp64) or "redblack32" (fp32).
+    Returns (residual_history ndarray, iterations_run, kernel_seconds).
+    """
+    lib = load()
+    if grid.dtype != np.float64 or not grid.flags.c_contiguous or grid.ndim != 2:
+        raise ValueError("grid must be a C-contiguous float64 2-D array")
+    rows, cols = grid.shape
+    nh = _as_f64(noise_h, (rows, cols - 1), "noise_h")
+    nv = _as_f64(noise_v, (rows - 1, cols), "noise_v")
+    src = _as_f64(source, (rows, cols), "source")
+    max_iter = int(max_iter)
+    hist = np.zeros(max(max_iter, 1), dtype=np.float64)
+    iters = ctypes.c_int64(0)
+    ksec = ctypes.c_double(0.0)
+    head = (_ptr(grid), _ptr(nh), _ptr(nv), _ptr(src), rows, cols, float(tol), max_iter)
+    if mode == "exact":
+        rc = lib.apde_solve_exact_f64_path(*head, _ptr(hist), ctypes.byref(iters), ctypes.byref(ksec),
+                                           EXACT_PATHS[exact_path])
+    elif mode in ("redblack", "redblack64"):
+        rc = lib.apde_solve_redblack_f64(*head, int(check_every), int(temporal_depth), _ptr(hist),
+                                         ctypes.byref(iters), ctypes.byref(ksec))
+    elif mode == "redblack32":
+        rc = lib.apde_solve_redblack_f32(*head, int(check_every), int(temporal_depth), _ptr(hist),
+                                         ctypes.byref(iters), ctypes.byref(ksec))
+    else:
+        raise ValueError(f"unknown APDE mode {mode!r} (exact | redblack | redblack32)")
+    check(rc)
+    n = int(iters.value)
+    return hist[:max(n, 0)].copy(), n, float(ksec.value)
+
+
+class Plan:
+    """Device-resident row strip of a global grid (apde_plan_* in include/apde.h)."""
+
+    def __init__(self, grows: int, cols: int, row_begin: int = 0, row_end: Optional[int] = None,
+                 dtype=np.float64, has_noise: bool = False, has_source: bool = False,
+                 temporal_depth: int = 4):
+        self._lib = load()
+        self.dtype = np.dtype(dtype)
+        if self.dtype not in (np.dtype(np.float64), np.dtype(np.float32)):
+            raise ValueError("dtype must be float32 or float64")
+        row_end = grows if row_end is None else row_end
+        self.desc = PlanDesc(self.dtype.itemsize, int(has_noise), int(has_source), int(temporal_depth),
+                             int(grows), int(cols), int(row_begin), int(row_end))
+        self._h = _vp(None)
+        check(self._lib.apde_plan_create(ctypes.byref(self._h), ctypes.byref(self.desc)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.apde_plan_destroy(self._h)
+            self._h = _vp(None)
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def upload(self, grid, noise_h=None, noise_v=None, source=None):
+        g, c = self.desc.grows, self.desc.cols
+        grid = _as_f64(grid, (g, c), "grid")
+        check(self._lib.apde_plan_upload(self._h, _ptr(grid), _ptr(_as_f64(noise_h, (g, c - 1), "noise_h")),
+                                         _ptr(_as_f64(noise_v, (g - 1, c), "noise_v")),
+                                         _ptr(_as_f64(source, (g, c), "source"))))
+
+    def fill(self, kind: int = 0, top_hot: bool = False, noise_level: float = 0.0, seed: int = 0):
+        f = FillDesc(int(kind), int(top_hot), float(noise_level), int(seed))
+        check(self._lib.apde_plan_fill(self._h, ctypes.byref(f)))
+
+    def download(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        g, c = self.desc.grows, self.desc.cols
+        if out is None:
+            out = np.zeros((g, c), dtype=np.float64)
+        check(self._lib.apde_plan_download(self._h, _ptr(out)))
+        return out
+
+    def run(self, n_sweeps: int, sweep_base: int = 0, phase: int = 0, stream: int = 0):
+        check(self._lib.apde_plan_run(self._h, int(n_sweeps), int(sweep_base), int(phase), _vp(stream)))
+
+    def halo(self, side: int):
+        s, r, n = _vp(None), _vp(None), ctypes.c_int64(0)
+        check(self._lib.apde_plan_halo(self._h, int(side), ctypes.byref(s), ctypes.byref(r), ctypes.byref(n)))
+        return s.value, r.value, int(n.value)
+
+    def residuals(self, first: int, count: int, stream: int = 0) -> np.ndarray:
+        out = np.zeros(max(int(count), 1), dtype=np.float64)
+        check(self._lib.apde_plan_read_residuals(self._h, int(first), int(count), _ptr(out), _vp(stream)))
+        return out[:count]
+
+    def checksum(self, stream: int = 0):
+        s, m = ctypes.c_double(0.0), ctypes.c_double(0.0)
+        check(self._lib.apde_plan_checksum(self._h, ctypes.byref(s), ctypes.byref(m), _vp(stream)))
+        return float(s.value), float(m.value)
+
+    @property
+    def launches(self) -> int:
+        return int(self._lib.apde_plan_launch_count(self._h))

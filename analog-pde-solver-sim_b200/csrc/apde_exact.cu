@@ -1,0 +1,571 @@
+// apde_exact.cu -- bit-exact lexicographic Gauss-Seidel on sm_100a.
+//
+// THIS TRANSLATION UNIT MUST BE COMPILED WITH  -fmad=false .
+//
+// It replaces the reference's sweep loops
+//   AnalogPDESolver.solve  analog_pde_solver/solver.py:263-287
+//   DigitalSolver.solve    analog_pde_solver/solver.py:344-368
+// and reproduces every iterate bit for bit.  The reference updates nodes in row-major
+// order in place, so node (i,j) of sweep t reads NEW north/west (sweep t) and OLD
+// south/east (sweep t-1).  All nodes with the same  s = 2t + i + j  are independent:
+//   north/west of (t,i,j) have s-1, south/east of sweep t-1 have s-1, own old value s-2.
+// Both kernels below walk s ("time-skewed anti-diagonal wavefront"), so many sweeps are
+// in flight at once, and every operand is exactly the value the serial loop would read.
+//
+// Arithmetic per node (solver.py:269-279), one IEEE rounding per operation:
+//   n = u[i-1,j]/nv[i-1,j]; s = u[i+1,j]/nv[i,j]; w = u[i,j-1]/nh[i,j-1]; e = u[i,j+1]/nh[i,j]
+//   new = ((((n+s)+w)+e)-src)/4.0 ; change = |new-old| ; max_change = max (NaN ignored)
+// The fp64 '/' of CUDA is IEEE-correct; /4.0 is exact either way.
+//
+// K1  exact_small_kernel : whole problem in one CTA's shared memory, all sweeps of a batch
+//                          pipelined over s, early stop + rollback inside the kernel.
+// K2  exact_ring_kernel  : large grids, anti-diagonal-major layout in HBM/L2, one sweep per
+//                          CTA, CTAs chained in a ring by acquire/release progress counters
+//                          (CTA of sweep t trails CTA of sweep t-1 by one diagonal).
+#include <algorithm>
+#include <vector>
+
+#include "apde_common.h"
+
+namespace apde {
+
+// ------------------------------------------------------------------------------------------
+// the node update, shared by K1 and K2
+// ------------------------------------------------------------------------------------------
+template <bool HAS_NOISE, bool HAS_SRC>
+__device__ __forceinline__ double relax_node(double un, double us, double uw, double ue,
+                                             double ln, double ls, double lw, double le,
+                                             double src) {
+    if (HAS_NOISE) {
+        un = __ddiv_rn(un, ln);  // solver.py:269
+        us = __ddiv_rn(us, ls);  // :270
+        uw = __ddiv_rn(uw, lw);  // :271
+        ue = __ddiv_rn(ue, le);  // :272
+    }
+    double acc = __dadd_rn(un, us);  // :275, left-associative
+    acc = __dadd_rn(acc, uw);
+    acc = __dadd_rn(acc, ue);
+    if (HAS_SRC) acc = __dsub_rn(acc, src);
+    return __dmul_rn(acc, 0.25);  // == /4.0 exactly
+}
+
+// ==========================================================================================
+// K1: one CTA, problem resident in shared memory
+// ==========================================================================================
+constexpr int K1_MAX_BATCH = 256;
+
+struct K1Params {
+    double *grid;          // rows*cols row-major (in: BC + initial guess, out: solution)
+    const double *nh;      // rows*(cols-1) or null
+    const double *nv;      // (rows-1)*cols or null
+    const double *src;     // rows*cols or null
+    double *snapshot;      // rows*cols scratch (rollback state)
+    double *hist;          // capacity max_iter
+    long long *iters_out;  // iterations_run
+    int rows, cols;
+    int batch;             // sweeps pipelined per drained batch (<= K1_MAX_BATCH)
+    long long max_iter;
+    double tol;
+};
+
+template <bool HAS_NOISE, bool HAS_SRC>
+__device__ __forceinline__ void k1_run_batch(double *u, const double *nh, const double *nv,
+                                             const double *src, double *slots, int rows,
+                                             int cols, int nb) {
+    const int hw = (cols - 1) / 2;  // candidate columns per row and parity
+    const int dmax = rows + cols - 4;
+    const int s_end = 2 * (nb - 1) + dmax;
+    for (int k = threadIdx.y * blockDim.x + threadIdx.x; k < nb; k += blockDim.x * blockDim.y)
+        slots[k] = 0.0;
+    __syncthreads();
+    for (int s = 2; s <= s_end; ++s) {
+        const int p = s & 1;
+        for (int i = 1 + threadIdx.y; i <= rows - 2; i += blockDim.y) {
+            const int off = (i + 1 + p) & 1;
+            for (int jj = threadIdx.x; jj < hw; jj += blockDim.x) {
+                const int j = 1 + 2 * jj + off;
+                if (j > cols - 2) continue;
+                const int tt = (s - i - j) >> 1;  // sweep (relative to the batch) this node is in
+                if (tt < 0 || tt >= nb || (s - i - j) < 0) continue;
+                const int c = i * cols + j;
+                double ln = 1.0, ls = 1.0, lw = 1.0, le = 1.0, sv = 0.0;
+                if (HAS_NOISE) {
+                    ln = nv[c - cols];
+                    ls = nv[c];
+                    lw = nh[i * (cols - 1) + j - 1];
+                    le = nh[i * (cols - 1) + j];
+                }
+                if (HAS_SRC) sv = src[c];
+                const double old = u[c];
+                const double nw = relax_node<HAS_NOISE, HAS_SRC>(u[c - cols], u[c + cols], u[c - 1],
+                                                                 u[c + 1], ln, ls, lw, le, sv);
+                const double ch = fabs(__dsub_rn(nw, old));
+                u[c] = nw;
+                // strict '>' like solver.py:277 (NaN never enters); skip the atomic when it cannot win
+                if (ch > slots[tt]) atomic_max_nonneg(&slots[tt], ch);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <bool HAS_NOISE, bool HAS_SRC>
+__global__ void __launch_bounds__(1024, 1) exact_small_kernel(K1Params p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int rows = p.rows, cols = p.cols;
+    const int n = rows * cols;
+    double *u = reinterpret_cast<double *>(smem_raw);
+    double *slots = u + n;
+    double *cur = slots + K1_MAX_BATCH;
+    double *nh = nullptr, *nv = nullptr, *src = nullptr;
+    if (HAS_NOISE) {
+        nh = cur;
+        cur += rows * (cols - 1);
+        nv = cur;
+        cur += (rows - 1) * cols;
+    }
+    if (HAS_SRC) src = cur;
+    __shared__ int sh_stop;  // -1: no stop in this batch, else index of first converged sweep
+
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int nthr = blockDim.x * blockDim.y;
+    for (int k = tid; k < n; k += nthr) u[k] = p.grid[k];
+    if (HAS_NOISE) {
+        for (int k = tid; k < rows * (cols - 1); k += nthr) nh[k] = p.nh[k];
+        for (int k = tid; k < (rows - 1) * cols; k += nthr) nv[k] = p.nv[k];
+    }
+    if (HAS_SRC)
+        for (int k = tid; k < n; k += nthr) src[k] = p.src[k];
+    __syncthreads();
+
+    const bool may_stop = p.tol > 0.0;  // max_change >= 0 is never < tol otherwise (NaN tol: never)
+    long long t0 = 0;
+    long long iters = p.max_iter;  // for...else of solver.py:286-287
+    while (t0 < p.max_iter) {
+        const long long left = p.max_iter - t0;
+        const int nb = left < p.batch ? (int)left : p.batch;
+        if (may_stop) {
+            for (int k = tid; k < n; k += nthr) p.snapshot[k] = u[k];
+        }
+        k1_run_batch<HAS_NOISE, HAS_SRC>(u, nh, nv, src, slots, rows, cols, nb);
+        if (tid == 0) {
+            int stop = -1;
+            if (may_stop)
+                for (int k = 0; k < nb; ++k)
+                    if (slots[k] < p.tol) {  // solver.py:283
+                        stop = k;
+                        break;
+                    }
+            sh_stop = stop;
+        }
+        __syncthreads();
+        const int stop = sh_stop;
+        const int keep = stop < 0 ? nb : stop + 1;
+        for (int k = tid; k < keep; k += nthr) p.hist[t0 + k] = slots[k];  // solver.py:281
+        if (stop >= 0) {
+            if (stop != nb - 1) {
+                // sweeps after the stopping one already touched the grid: roll back and replay
+                // exactly stop+1 sweeps (deterministic, so the replay is bit-identical).
+                __syncthreads();
+                for (int k = tid; k < n; k += nthr) u[k] = p.snapshot[k];
+                __syncthreads();
+                k1_run_batch<HAS_NOISE, HAS_SRC>(u, nh, nv, src, slots, rows, cols, stop + 1);
+            }
+            iters = t0 + stop + 1;  // solver.py:284
+            break;
+        }
+        t0 += nb;
+        __syncthreads();
+    }
+    __syncthreads();
+    for (int k = tid; k < n; k += nthr) p.grid[k] = u[k];
+    if (tid == 0) *p.iters_out = iters;
+}
+
+// ==========================================================================================
+// K2: ring of CTAs over an anti-diagonal-major layout
+//   A[d][i] (pitch P) holds the value of node (i, j = d - i); for a node on diagonal d:
+//     north (i-1,j) = U[d-1][i-1]   west (i,j-1) = U[d-1][i]
+//     south (i+1,j) = U[d+1][i+1]   east (i,j+1) = U[d+1][i]
+//     link arrays in node layout: LV[d][i] = nv[i,j] (link to south), LH[d][i] = nh[i,j] (link to east)
+//     north link = LV[d-1][i-1], west link = LH[d-1][i], south link = LV[d][i], east link = LH[d][i]
+//   every access is unit-stride in i.
+// ==========================================================================================
+__global__ void to_diag_kernel(const double *__restrict__ rm, double *__restrict__ dm, int rows,
+                               int cols, int P) {
+    // rm is rows x cols row-major (its own dims); dm[(i+j)*P + i]
+    const long long n = (long long)rows * cols;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n;
+         k += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(k / cols), j = (int)(k - (long long)i * cols);
+        dm[(long long)(i + j) * P + i] = rm[k];
+    }
+}
+__global__ void from_diag_kernel(const double *__restrict__ dm, double *__restrict__ rm, int rows,
+                                 int cols, int P) {
+    const long long n = (long long)rows * cols;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n;
+         k += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(k / cols), j = (int)(k - (long long)i * cols);
+        rm[k] = dm[(long long)(i + j) * P + i];
+    }
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+struct K2Params {
+    double *U;
+    const double *LH, *LV, *S;
+    double *hist;                   // this launch's first sweep
+    unsigned long long *progress;   // one counter per CTA (stride 16 to keep them on separate lines)
+    int rows, cols, P;
+    long long n_sweeps;             // sweeps in this launch
+};
+
+template <bool HAS_NOISE, bool HAS_SRC>
+__global__ void __launch_bounds__(1024, 1) exact_ring_kernel(K2Params p) {
+    const int rows = p.rows, cols = p.cols;
+    const long long P = p.P;
+    const int G = gridDim.x, c = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+    const int dmax = rows + cols - 4;
+    const long long ND = dmax - 1;  // diagonals 2..dmax
+    const int pred = (c + G - 1) % G;
+    __shared__ double red[32];
+    double *__restrict__ U = p.U;
+
+    long long m = 0;
+    for (long long t = c; t < p.n_sweeps; t += G, ++m) {
+        const long long mpred = (c == 0) ? m - 1 : m;  // index of sweep t-1 in pred's own sequence
+        double mx = 0.0;
+        for (int d = 2; d <= dmax; ++d) {
+            if (t > 0 && tid == 0) {
+                // sweep t-1 must have finished diagonal d+1 (RAW on south/east, WAR on this diagonal)
+                const unsigned long long need =
+                    (unsigned long long)(mpred * ND + (long long)(min(d + 1, dmax) - 1));
+                const unsigned long long *flag = p.progress + (size_t)pred * 16;
+                while (ld_acquire_u64(flag) < need) {
+                }
+            }
+            __syncthreads();
+            const int ilo = max(1, d - (cols - 2)), ihi = min(rows - 2, d - 1);
+            const double *up = U + (long long)(d - 1) * P;  // diagonal d-1: north/west, this sweep
+            const double *dn = U + (long long)(d + 1) * P;  // diagonal d+1: south/east, previous sweep
+            double *me = U + (long long)d * P;
+            for (int i = ilo + tid; i <= ihi; i += nthr) {
+                const double un = __ldcg(up + i - 1), uw = __ldcg(up + i);
+                const double us = __ldcg(dn + i + 1), ue = __ldcg(dn + i);
+                const double old = __ldcg(me + i);
+                double ln = 1.0, ls = 1.0, lw = 1.0, le = 1.0, sv = 0.0;
+                if (HAS_NOISE) {
+                    ln = __ldg(p.LV + (long long)(d - 1) * P + i - 1);
+                    lw = __ldg(p.LH + (long long)(d - 1) * P + i);
+                    ls = __ldg(p.LV + (long long)d * P + i);
+                    le = __ldg(p.LH + (long long)d * P + i);
+                }
+                if (HAS_SRC) sv = __ldg(p.S + (long long)d * P + i);
+                const double nw = relax_node<HAS_NOISE, HAS_SRC>(un, us, uw, ue, ln, ls, lw, le, sv);
+                mx = max_ignore_nan(mx, fabs(__dsub_rn(nw, old)));
+                __stcg(me + i, nw);
+            }
+            __syncthreads();
+            if (tid == 0)
+                st_release_u64(p.progress + (size_t)c * 16, (unsigned long long)(m * ND + (d - 1)));
+        }
+        // block max of this sweep -> residual_history[t]   (solver.py:281)
+        mx = warp_max(mx);
+        if ((tid & 31) == 0) red[tid >> 5] = mx;
+        __syncthreads();
+        if (tid < 32) {
+            double v = (tid < (nthr + 31) / 32) ? red[tid] : 0.0;
+            v = warp_max(v);
+            if (tid == 0) p.hist[t] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host drivers
+// ------------------------------------------------------------------------------------------
+template <typename K>
+static int max_dyn_smem(K kernel, size_t bytes) {
+    APDE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return APDE_OK;
+}
+
+static size_t k1_smem_bytes(int64_t rows, int64_t cols, bool noise, bool src) {
+    size_t n = (size_t)rows * cols;
+    size_t d = n + K1_MAX_BATCH;
+    if (noise) d += (size_t)rows * (cols - 1) + (size_t)(rows - 1) * cols;
+    if (src) d += n;
+    return d * sizeof(double);
+}
+
+static int solve_small(double *grid, const double *nh, const double *nv, const double *src,
+                       int64_t rows, int64_t cols, double tol, int64_t max_iter, double *hist,
+                       int64_t *iters, double *ksec) {
+    const bool noise = nh != nullptr, has_src = src != nullptr;
+    const size_t n = (size_t)rows * cols;
+    DevBuf d_grid, d_nh, d_nv, d_src, d_snap, d_hist, d_iters;
+    APDE_TRY(d_grid.alloc(n * 8));
+    APDE_TRY(d_snap.alloc(n * 8));
+    APDE_TRY(d_hist.alloc((size_t)max_iter * 8));
+    APDE_TRY(d_iters.alloc(8));
+    APDE_CUDA(cudaMemcpy(d_grid.p, grid, n * 8, cudaMemcpyHostToDevice));
+    if (noise) {
+        APDE_TRY(d_nh.alloc((size_t)rows * (cols - 1) * 8));
+        APDE_TRY(d_nv.alloc((size_t)(rows - 1) * cols * 8));
+        APDE_CUDA(cudaMemcpy(d_nh.p, nh, (size_t)rows * (cols - 1) * 8, cudaMemcpyHostToDevice));
+        APDE_CUDA(cudaMemcpy(d_nv.p, nv, (size_t)(rows - 1) * cols * 8, cudaMemcpyHostToDevice));
+    }
+    if (has_src) {
+        APDE_TRY(d_src.alloc(n * 8));
+        APDE_CUDA(cudaMemcpy(d_src.p, src, n * 8, cudaMemcpyHostToDevice));
+    }
+    K1Params p;
+    p.grid = d_grid.as<double>();
+    p.nh = d_nh.as<double>();
+    p.nv = d_nv.as<double>();
+    p.src = d_src.as<double>();
+    p.snapshot = d_snap.as<double>();
+    p.hist = d_hist.as<double>();
+    p.iters_out = d_iters.as<long long>();
+    p.rows = (int)rows;
+    p.cols = (int)cols;
+    p.max_iter = max_iter;
+    p.tol = tol;
+    const int nd = (int)(rows + cols - 5);
+    p.batch = std::min(K1_MAX_BATCH, std::max(16, 2 * nd));
+
+    const int hw = (int)(cols - 1) / 2;
+    int bx = 1;
+    while (bx < hw && bx < 32) bx <<= 1;
+    int by = (int)std::min<int64_t>(rows - 2, 1024 / bx);
+    if (by < 1) by = 1;
+    dim3 block(bx, by);
+    const size_t smem = k1_smem_bytes(rows, cols, noise, has_src);
+
+    EventPair ev;
+    APDE_TRY(ev.init());
+#define K1_LAUNCH(N, S)                                                                 \
+    do {                                                                                \
+        APDE_TRY(max_dyn_smem(exact_small_kernel<N, S>, smem));                         \
+        APDE_CUDA(cudaEventRecord(ev.a));                                               \
+        exact_small_kernel<N, S><<<1, block, smem>>>(p);                                \
+        APDE_CUDA(cudaEventRecord(ev.b));                                               \
+    } while (0)
+    if (noise && has_src) K1_LAUNCH(true, true);
+    else if (noise) K1_LAUNCH(true, false);
+    else if (has_src) K1_LAUNCH(false, true);
+    else K1_LAUNCH(false, false);
+#undef K1_LAUNCH
+    APDE_CUDA(cudaGetLastError());
+    APDE_CUDA(cudaEventSynchronize(ev.b));
+    float ms = 0.f;
+    APDE_CUDA(cudaEventElapsedTime(&ms, ev.a, ev.b));
+    if (ksec) *ksec = ms * 1e-3;
+    long long it = 0;
+    APDE_CUDA(cudaMemcpy(&it, d_iters.p, 8, cudaMemcpyDeviceToHost));
+    *iters = it;
+    if (it > 0) APDE_CUDA(cudaMemcpy(hist, d_hist.p, (size_t)it * 8, cudaMemcpyDeviceToHost));
+    APDE_CUDA(cudaMemcpy(grid, d_grid.p, n * 8, cudaMemcpyDeviceToHost));
+    return APDE_OK;
+}
+
+template <bool N, bool S>
+static int ring_launch(const K2Params &p, int grid, int block, cudaStream_t st) {
+    void *args[] = {(void *)&p};
+    APDE_CUDA(cudaLaunchCooperativeKernel((void *)exact_ring_kernel<N, S>, dim3(grid), dim3(block),
+                                          args, 0, st));
+    return APDE_OK;
+}
+
+static int ring_dispatch(bool noise, bool src, const K2Params &p, int grid, int block,
+                         cudaStream_t st) {
+    if (noise && src) return ring_launch<true, true>(p, grid, block, st);
+    if (noise) return ring_launch<true, false>(p, grid, block, st);
+    if (src) return ring_launch<false, true>(p, grid, block, st);
+    return ring_launch<false, false>(p, grid, block, st);
+}
+
+static int ring_occupancy(bool noise, bool src, int block, int *per_sm) {
+    if (noise && src)
+        APDE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, exact_ring_kernel<true, true>, block, 0));
+    else if (noise)
+        APDE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, exact_ring_kernel<true, false>, block, 0));
+    else if (src)
+        APDE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, exact_ring_kernel<false, true>, block, 0));
+    else
+        APDE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, exact_ring_kernel<false, false>, block, 0));
+    return APDE_OK;
+}
+
+static int solve_ring(double *grid, const double *nh, const double *nv, const double *src,
+                      int64_t rows, int64_t cols, double tol, int64_t max_iter, double *hist,
+                      int64_t *iters, double *ksec, const cudaDeviceProp &prop) {
+    const bool noise = nh != nullptr, has_src = src != nullptr;
+    const size_t n = (size_t)rows * cols;
+    const int P = (int)((rows + 3) & ~(int64_t)3);
+    const size_t nd_total = (size_t)(rows + cols - 1);
+    const size_t dbytes = nd_total * (size_t)P * 8;
+
+    DevBuf stage, U, LH, LV, S, snap, d_hist, d_prog;
+    APDE_TRY(stage.alloc(n * 8));
+    APDE_TRY(U.alloc(dbytes));
+    APDE_CUDA(cudaMemset(U.p, 0, dbytes));
+    const int tb = 256, tg = prop.multiProcessorCount * 8;
+    APDE_CUDA(cudaMemcpy(stage.p, grid, n * 8, cudaMemcpyHostToDevice));
+    to_diag_kernel<<<tg, tb>>>(stage.as<double>(), U.as<double>(), (int)rows, (int)cols, P);
+    if (noise) {
+        APDE_TRY(LH.alloc(dbytes));
+        APDE_TRY(LV.alloc(dbytes));
+        // pad with 1.0 bit patterns is unnecessary: only valid links are ever read
+        APDE_CUDA(cudaMemset(LH.p, 0, dbytes));
+        APDE_CUDA(cudaMemset(LV.p, 0, dbytes));
+        APDE_CUDA(cudaMemcpy(stage.p, nh, (size_t)rows * (cols - 1) * 8, cudaMemcpyHostToDevice));
+        to_diag_kernel<<<tg, tb>>>(stage.as<double>(), LH.as<double>(), (int)rows, (int)cols - 1, P);
+        APDE_CUDA(cudaMemcpy(stage.p, nv, (size_t)(rows - 1) * cols * 8, cudaMemcpyHostToDevice));
+        to_diag_kernel<<<tg, tb>>>(stage.as<double>(), LV.as<double>(), (int)rows - 1, (int)cols, P);
+    }
+    if (has_src) {
+        APDE_TRY(S.alloc(dbytes));
+        APDE_CUDA(cudaMemset(S.p, 0, dbytes));
+        APDE_CUDA(cudaMemcpy(stage.p, src, n * 8, cudaMemcpyHostToDevice));
+        to_diag_kernel<<<tg, tb>>>(stage.as<double>(), S.as<double>(), (int)rows, (int)cols, P);
+    }
+    APDE_CUDA(cudaGetLastError());
+    APDE_TRY(d_hist.alloc((size_t)max_iter * 8));
+
+    // block size: longest diagonal decides; two resident CTAs per SM hide each other's latency
+    const int64_t maxdiag = std::min(rows, cols) - 2;
+    int block = maxdiag > 2048 ? 1024 : (maxdiag > 512 ? 512 : 256);
+    int per_sm = 0;
+    APDE_TRY(ring_occupancy(noise, has_src, block, &per_sm));
+    if (per_sm < 1) {
+        set_error("exact_ring_kernel cannot be resident (block=%d)", block);
+        return APDE_ECUDA;
+    }
+    const int gmax = per_sm * prop.multiProcessorCount;
+    APDE_TRY(d_prog.alloc((size_t)gmax * 16 * 8));
+
+    const bool may_stop = tol > 0.0;
+    if (may_stop) APDE_TRY(snap.alloc(dbytes));
+    const int64_t nd = rows + cols - 5;
+    // sweeps per launch when convergence has to be checked: enough to amortise the pipeline
+    // fill/drain (2 diagonals per in-flight sweep) against nd diagonals per sweep
+    int64_t chunk_cap = gmax;
+    while (chunk_cap * 2 <= 4096 && 2 * (int64_t)gmax > nd && chunk_cap < 8 * (int64_t)gmax) chunk_cap *= 2;
+
+    EventPair ev;
+    APDE_TRY(ev.init());
+    float total_ms = 0.f;
+    K2Params p;
+    p.U = U.as<double>();
+    p.LH = LH.as<double>();
+    p.LV = LV.as<double>();
+    p.S = S.as<double>();
+    p.progress = d_prog.as<unsigned long long>();
+    p.rows = (int)rows;
+    p.cols = (int)cols;
+    p.P = P;
+
+    std::vector<double> hbuf;
+    int64_t done = 0, result_iters = max_iter;
+    while (done < max_iter) {
+        const int64_t chunk = may_stop ? std::min<int64_t>(max_iter - done, chunk_cap) : (max_iter - done);
+        const int g = (int)std::min<int64_t>(chunk, gmax);
+        if (may_stop) APDE_CUDA(cudaMemcpyAsync(snap.p, U.p, dbytes, cudaMemcpyDeviceToDevice, 0));
+        APDE_CUDA(cudaMemsetAsync(d_prog.p, 0, d_prog.bytes, 0));
+        p.hist = d_hist.as<double>() + done;
+        p.n_sweeps = chunk;
+        APDE_CUDA(cudaEventRecord(ev.a));
+        APDE_TRY(ring_dispatch(noise, has_src, p, g, block, 0));
+        APDE_CUDA(cudaEventRecord(ev.b));
+        APDE_CUDA(cudaEventSynchronize(ev.b));
+        float ms = 0.f;
+        APDE_CUDA(cudaEventElapsedTime(&ms, ev.a, ev.b));
+        total_ms += ms;
+        if (may_stop) {
+            hbuf.resize((size_t)chunk);
+            APDE_CUDA(cudaMemcpy(hbuf.data(), p.hist, (size_t)chunk * 8, cudaMemcpyDeviceToHost));
+            int64_t stop = -1;
+            for (int64_t k = 0; k < chunk; ++k)
+                if (hbuf[(size_t)k] < tol) {  // solver.py:283
+                    stop = k;
+                    break;
+                }
+            if (stop >= 0) {
+                if (stop != chunk - 1) {
+                    // later sweeps of the chunk already ran: roll back, replay exactly stop+1 sweeps
+                    APDE_CUDA(cudaMemcpyAsync(U.p, snap.p, dbytes, cudaMemcpyDeviceToDevice, 0));
+                    APDE_CUDA(cudaMemsetAsync(d_prog.p, 0, d_prog.bytes, 0));
+                    p.n_sweeps = stop + 1;
+                    APDE_CUDA(cudaEventRecord(ev.a));
+                    APDE_TRY(ring_dispatch(noise, has_src, p, (int)std::min<int64_t>(stop + 1, gmax), block, 0));
+                    APDE_CUDA(cudaEventRecord(ev.b));
+                    APDE_CUDA(cudaEventSynchronize(ev.b));
+                    APDE_CUDA(cudaEventElapsedTime(&ms, ev.a, ev.b));
+                    total_ms += ms;
+                }
+                result_iters = done + stop + 1;
+                break;
+            }
+        }
+        done += chunk;
+    }
+    *iters = result_iters;
+    if (ksec) *ksec = total_ms * 1e-3;
+    if (result_iters > 0)
+        APDE_CUDA(cudaMemcpy(hist, d_hist.p, (size_t)result_iters * 8, cudaMemcpyDeviceToHost));
+    from_diag_kernel<<<tg, tb>>>(U.as<double>(), stage.as<double>(), (int)rows, (int)cols, P);
+    APDE_CUDA(cudaGetLastError());
+    APDE_CUDA(cudaMemcpy(grid, stage.p, n * 8, cudaMemcpyDeviceToHost));
+    return APDE_OK;
+}
+
+// entry used by the C-ABI (apde_api.cu)
+int solve_exact_f64(double *grid, const double *nh, const double *nv, const double *src,
+                    int64_t rows, int64_t cols, double tol, int64_t max_iter, double *hist,
+                    int64_t *iters, double *ksec, int force_path) {
+    if (ksec) *ksec = 0.0;
+    if (max_iter <= 0) {  // range(max_iter) is empty: for...else sets iterations_run = max_iter
+        *iters = max_iter;
+        return APDE_OK;
+    }
+    if (rows < 3 || cols < 3) {
+        // no interior node: every sweep has max_change == 0.0 (solver.py:264, :281-287)
+        const int64_t n = (0.0 < tol) ? 1 : max_iter;
+        for (int64_t k = 0; k < n; ++k) hist[k] = 0.0;
+        *iters = n;
+        return APDE_OK;
+    }
+    if (rows > (1 << 30) || cols > (1 << 30) || rows + cols > (1ll << 30)) {
+        set_error("exact path: grid %lld x %lld too large", (long long)rows, (long long)cols);
+        return APDE_EINVAL;
+    }
+    cudaDeviceProp prop;
+    APDE_TRY(require_sm100(&prop));
+    const size_t smem = k1_smem_bytes(rows, cols, nh != nullptr, src != nullptr);
+    const bool fits = smem + 1024 <= (size_t)prop.sharedMemPerBlockOptin;
+    bool small = fits;
+    if (force_path == 1) {
+        if (!fits) {
+            set_error("exact path: %lld x %lld does not fit the one-CTA kernel", (long long)rows, (long long)cols);
+            return APDE_EINVAL;
+        }
+        small = true;
+    } else if (force_path == 2) {
+        small = false;
+    }
+    if (small) return solve_small(grid, nh, nv, src, rows, cols, tol, max_iter, hist, iters, ksec);
+    return solve_ring(grid, nh, nv, src, rows, cols, tol, max_iter, hist, iters, ksec, prop);
+}
+
+}  // namespace apde

@@ -1,0 +1,51 @@
+// Device-resident row-strip plan for the red-black throughput path (internal header).
+#pragma once
+#include "apde_common.h"
+
+struct apde_plan {
+    apde_plan_desc d{};
+    int device = 0;
+    int sm_count = 0;
+    int elem = 8;             // dtype bytes
+    // geometry of the local (strip) arrays -----------------------------------------------------
+    int64_t halo = 0;         // ghost rows per interior side = 2 * temporal_depth
+    int64_t ghost_top = 0;    // ghost rows actually present above / below
+    int64_t ghost_bot = 0;
+    int64_t lrows = 0;        // ghost_top + owned + ghost_bot
+    int64_t row0 = 0;         // global row index of local row 0
+    int64_t padl = 0;         // zero columns left of column 0 (alignment + tile overhang)
+    int64_t pitch = 0;        // elements per local row
+    // buffers (all lrows x pitch, plan dtype) --------------------------------------------------
+    apde::DevBuf u[2];        // ping-pong grids; u[cur] is current
+    apde::DevBuf src, gh, gv; // source, 1/noise_h, 1/noise_v  (gh[i][j]: link (i,j)-(i,j+1); gv[i][j]: (i,j)-(i+1,j))
+    apde::DevBuf resid;       // per-sweep max_change, plan dtype
+    apde::DevBuf scratch;     // checksum outputs etc.
+    int cur = 0;
+    int64_t resid_cap = 0;
+    int64_t launches = 0;
+    bool filled = false;
+
+    size_t plane_elems() const { return (size_t)lrows * (size_t)pitch; }
+    // element offset of (local row li, column j)
+    size_t off(int64_t li, int64_t j) const { return (size_t)li * (size_t)pitch + (size_t)(padl + j); }
+};
+
+namespace apde {
+// implemented in apde_redblack.cu
+int plan_create(apde_plan **out, const apde_plan_desc *d);
+int plan_upload(apde_plan *p, const double *grid, const double *nh, const double *nv, const double *src);
+int plan_fill(apde_plan *p, const apde_fill_desc *f);
+int plan_download(apde_plan *p, double *grid);
+int plan_run(apde_plan *p, int64_t n_sweeps, int64_t sweep_base, int phase, cudaStream_t st);
+int plan_halo(apde_plan *p, int side, void **send_ptr, void **recv_ptr, int64_t *nbytes);
+int plan_read_residuals(apde_plan *p, int64_t first, int64_t count, double *out, cudaStream_t st);
+int plan_checksum(apde_plan *p, double *sum_out, double *absmax_out, cudaStream_t st);
+int plan_ensure_resid(apde_plan *p, int64_t cap);
+int solve_redblack(int elem, double *grid, const double *nh, const double *nv, const double *src,
+                   int64_t rows, int64_t cols, double tol, int64_t max_iter, int check_every,
+                   int temporal_depth, double *hist, int64_t *iters, double *ksec);
+// implemented in apde_exact.cu
+int solve_exact_f64(double *grid, const double *nh, const double *nv, const double *src,
+                    int64_t rows, int64_t cols, double tol, int64_t max_iter, double *hist,
+                    int64_t *iters, double *ksec, int force_path);
+}  // namespace apde

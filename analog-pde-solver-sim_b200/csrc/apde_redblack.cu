@@ -1,0 +1,598 @@
+// apde_redblack.cu -- red-black Gauss-Seidel throughput path on sm_100a (fp64 / fp32).
+//
+// Same fixed point as the reference sweeps (analog_pde_solver/solver.py:263-287, :344-368) but
+// relaxed colour by colour ((i+j) even first), so every node of a colour is independent.
+// Per node, with conductances g = 1/noise precomputed once (recip kernel):
+//     acc = gN*uN; acc = fma(gS,uS,acc); acc = fma(gW,uW,acc); acc = fma(gE,uE,acc)     (mismatch)
+//     acc = ((uN+uS)+uW)+uE                                                           (no mismatch; solver.py:350-356 tree)
+//     acc = acc - src ; new = acc*0.25 ; change = |new-old|
+// All arithmetic uses explicit round-to-nearest intrinsics so that every kernel variant and the
+// CPU checker used by the tests (its red-black functions) produce identical bits.
+//
+// Strip layout (see apde_plan.h): lrows x pitch elements, `padl` zero columns left of column 0,
+// ghost rows above/below when the strip has neighbours.  Local row 0 and lrows-1 are never
+// updated (they are the global Dirichlet ring, or the outermost ghost row).
+#include <algorithm>
+#include <cmath>
+#include <new>
+#include <vector>
+
+#include "apde_plan.h"
+
+namespace apde {
+
+// ------------------------------------------------------------------------------------------
+// arithmetic traits
+// ------------------------------------------------------------------------------------------
+template <typename T> struct Ar;
+template <> struct Ar<double> {
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+    static __device__ __forceinline__ double abs(double a) { return fabs(a); }
+};
+template <> struct Ar<float> {
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+    static __device__ __forceinline__ float abs(float a) { return fabsf(a); }
+};
+
+template <typename T, bool NOISE, bool SRC>
+__device__ __forceinline__ T rb_relax(T un, T us, T uw, T ue, T gn, T gs, T gw, T ge, T sv) {
+    T acc;
+    if (NOISE) {
+        acc = Ar<T>::mul(gn, un);
+        acc = Ar<T>::fma(gs, us, acc);
+        acc = Ar<T>::fma(gw, uw, acc);
+        acc = Ar<T>::fma(ge, ue, acc);
+    } else {
+        acc = Ar<T>::add(un, us);
+        acc = Ar<T>::add(acc, uw);
+        acc = Ar<T>::add(acc, ue);
+    }
+    if (SRC) acc = Ar<T>::sub(acc, sv);
+    return Ar<T>::mul(acc, (T)0.25);
+}
+
+struct Geo {
+    long long pitch, padl;
+    long long lrows, cols, grows;
+    long long row0;        // global row of local row 0
+    long long own_lo, own_hi;  // owned local rows [own_lo, own_hi)
+};
+
+// ==========================================================================================
+// v0: one launch per colour, in place.  Baseline / cross-check variant (40 B/LUP at fp64).
+// ==========================================================================================
+template <typename T, bool NOISE, bool SRC>
+__global__ void __launch_bounds__(256) rb_colour_kernel(T *__restrict__ u, const T *__restrict__ src,
+                                                        const T *__restrict__ gh,
+                                                        const T *__restrict__ gv, Geo g, int colour,
+                                                        T *resid_slot) {
+    const long long hw = (g.cols - 1) / 2;
+    const long long jj = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    T mx = (T)0;
+    for (long long li = 1 + blockIdx.y; li <= g.lrows - 2; li += gridDim.y) {
+        const long long gi = g.row0 + li;
+        if (gi <= 0 || gi >= g.grows - 1) continue;  // ring rows never move
+        const long long j = 1 + 2 * jj + ((gi + 1 + colour) & 1);
+        if (jj < hw && j <= g.cols - 2) {
+            const long long c = li * g.pitch + g.padl + j;
+            T gn = (T)1, gs = (T)1, gw = (T)1, ge = (T)1, sv = (T)0;
+            if (NOISE) {
+                gn = gv[c - g.pitch];
+                gs = gv[c];
+                gw = gh[c - 1];
+                ge = gh[c];
+            }
+            if (SRC) sv = src[c];
+            const T old = u[c];
+            const T nw = rb_relax<T, NOISE, SRC>(u[c - g.pitch], u[c + g.pitch], u[c - 1], u[c + 1],
+                                                 gn, gs, gw, ge, sv);
+            u[c] = nw;
+            if (li >= g.own_lo && li < g.own_hi) mx = max_ignore_nan(mx, Ar<T>::abs(Ar<T>::sub(nw, old)));
+        }
+    }
+    __shared__ T red[8];
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        T v = threadIdx.x < 8 ? red[threadIdx.x] : (T)0;
+        v = warp_max(v);
+        if (threadIdx.x == 0 && v > (T)0) atomic_max_nonneg(resid_slot, v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// helpers: conversion / reciprocal / fill / checksum
+// ------------------------------------------------------------------------------------------
+// host float64 row-major (global) -> strip layout, plan dtype; recip => store 1/x (K5)
+template <typename T, bool RECIP>
+__global__ void pack_kernel(const double *__restrict__ in, long long in_rows, long long in_cols,
+                            long long in_row0 /*global row of in[0]*/, T *__restrict__ out, Geo g) {
+    const long long n = g.lrows * in_cols;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n;
+         k += (long long)gridDim.x * blockDim.x) {
+        const long long li = k / in_cols, j = k - li * in_cols;
+        const long long r = g.row0 + li - in_row0;
+        if (r < 0 || r >= in_rows) continue;
+        double v = in[r * in_cols + j];
+        if (RECIP) v = 1.0 / v;
+        out[li * g.pitch + g.padl + j] = (T)v;
+    }
+}
+template <typename T>
+__global__ void unpack_kernel(const T *__restrict__ in, Geo g, double *__restrict__ out,
+                              long long out_row0, long long out_rows) {
+    const long long nrows = g.own_hi - g.own_lo;
+    const long long n = nrows * g.cols;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n;
+         k += (long long)gridDim.x * blockDim.x) {
+        const long long r = k / g.cols, j = k - r * g.cols;
+        const long long li = g.own_lo + r;
+        const long long orow = g.row0 + li - out_row0;
+        if (orow < 0 || orow >= out_rows) continue;
+        out[orow * g.cols + j] = (double)in[li * g.pitch + g.padl + j];
+    }
+}
+
+// Philox4x32-10 (Salmon et al.), counter = link id, key = seed
+__device__ __forceinline__ void philox4x32_10(unsigned int c[4], unsigned int k0, unsigned int k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned int hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const unsigned int hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const unsigned int n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+__device__ __forceinline__ double philox_normal(unsigned long long id, unsigned long long seed) {
+    unsigned int c[4] = {(unsigned int)id, (unsigned int)(id >> 32), 0x41504445u /*'APDE'*/, 0u};
+    philox4x32_10(c, (unsigned int)seed, (unsigned int)(seed >> 32));
+    const double u1 = ((double)c[0] * 4294967296.0 + (double)c[1] + 0.5) * (1.0 / 18446744073709551616.0);
+    const double u2 = ((double)c[2] * 4294967296.0 + (double)c[3] + 0.5) * (1.0 / 18446744073709551616.0);
+    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
+
+template <typename T>
+__global__ void fill_kernel(T *__restrict__ u, T *__restrict__ src, T *__restrict__ gh,
+                            T *__restrict__ gv, Geo g, apde_fill_desc f) {
+    const long long n = g.lrows * g.cols;
+    const double PI = 3.14159265358979323846;
+    const long long m = (g.grows > g.cols ? g.grows : g.cols) - 1;
+    const double h = 1.0 / (double)m;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n;
+         k += (long long)gridDim.x * blockDim.x) {
+        const long long li = k / g.cols, j = k - li * g.cols;
+        const long long gi = g.row0 + li;
+        const long long c = li * g.pitch + g.padl + j;
+        u[c] = (f.top_hot && gi == 0) ? (T)1 : (T)0;
+        if (src) {
+            double s = 0.0;
+            if (f.kind == 1) {
+                const double x = (double)gi / (double)(g.grows - 1), y = (double)j / (double)(g.cols - 1);
+                s = (h * h) * (-2.0 * PI * PI * sin(PI * x) * sin(PI * y));
+            }
+            src[c] = (T)s;
+        }
+        if (gh) {
+            // gh[gi][j]: link (gi,j)-(gi,j+1), j < cols-1 ; gv[gi][j]: link (gi,j)-(gi+1,j), gi < grows-1
+            const unsigned long long idh = (unsigned long long)gi * (unsigned long long)g.cols + (unsigned long long)j;
+            const unsigned long long idv = idh + (unsigned long long)g.grows * (unsigned long long)g.cols;
+            double vh = 1.0, vv = 1.0;
+            if (f.noise_level > 0.0) {
+                vh = 1.0 / (1.0 + f.noise_level * philox_normal(idh, f.seed));
+                vv = 1.0 / (1.0 + f.noise_level * philox_normal(idv, f.seed));
+            }
+            gh[c] = (j < g.cols - 1) ? (T)vh : (T)0;
+            gv[c] = (gi < g.grows - 1) ? (T)vv : (T)0;
+        }
+    }
+}
+
+template <typename T>
+__global__ void checksum_kernel(const T *__restrict__ u, Geo g, double *out /*[0]=sum,[1]=absmax*/) {
+    const long long n = (g.own_hi - g.own_lo) * g.cols;
+    double s = 0.0, m = 0.0;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n;
+         k += (long long)gridDim.x * blockDim.x) {
+        const long long r = k / g.cols, j = k - r * g.cols;
+        const double v = (double)u[(g.own_lo + r) * g.pitch + g.padl + j];
+        s += v;
+        m = max_ignore_nan(m, fabs(v));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(out, s);
+        atomic_max_nonneg(out + 1, m);
+    }
+}
+
+template <typename T>
+__global__ void resid_to_f64_kernel(const T *in, double *out, long long n) {
+    const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (k < n) out[k] = (double)in[k];
+}
+
+// ------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------
+static Geo make_geo(const apde_plan *p) {
+    Geo g;
+    g.pitch = p->pitch;
+    g.padl = p->padl;
+    g.lrows = p->lrows;
+    g.cols = p->d.cols;
+    g.grows = p->d.grows;
+    g.row0 = p->row0;
+    g.own_lo = p->ghost_top;
+    g.own_hi = p->lrows - p->ghost_bot;
+    return g;
+}
+
+int plan_create(apde_plan **out, const apde_plan_desc *d) {
+    if (!out || !d) {
+        set_error("plan_create: NULL argument");
+        return APDE_EINVAL;
+    }
+    *out = nullptr;
+    if ((d->dtype_bytes != 4 && d->dtype_bytes != 8) || d->grows < 1 || d->cols < 1 ||
+        d->row_begin < 0 || d->row_end > d->grows || d->row_begin >= d->row_end ||
+        d->temporal_depth < 1 || d->temporal_depth > 16) {
+        set_error("plan_create: bad descriptor (dtype=%d grows=%lld cols=%lld rows=[%lld,%lld) depth=%d)",
+                  d->dtype_bytes, (long long)d->grows, (long long)d->cols, (long long)d->row_begin,
+                  (long long)d->row_end, d->temporal_depth);
+        return APDE_EINVAL;
+    }
+    cudaDeviceProp prop;
+    APDE_TRY(require_sm100(&prop));
+    apde_plan *p = new (std::nothrow) apde_plan();
+    if (!p) {
+        set_error("plan_create: out of host memory");
+        return APDE_ENOMEM;
+    }
+    p->d = *d;
+    APDE_CUDA(cudaGetDevice(&p->device));
+    p->sm_count = prop.multiProcessorCount;
+    p->elem = d->dtype_bytes;
+    p->halo = 2 * (int64_t)d->temporal_depth;
+    p->ghost_top = d->row_begin > 0 ? p->halo : 0;
+    p->ghost_bot = d->row_end < d->grows ? p->halo : 0;
+    const int64_t owned = d->row_end - d->row_begin;
+    if ((p->ghost_top || p->ghost_bot) && owned < p->halo) {
+        set_error("plan_create: strip of %lld rows is thinner than its halo (%lld)", (long long)owned,
+                  (long long)p->halo);
+        delete p;
+        return APDE_EINVAL;
+    }
+    if (d->row_begin - p->ghost_top < 0 || d->row_end + p->ghost_bot > d->grows) {
+        set_error("plan_create: halo reaches outside the global grid");
+        delete p;
+        return APDE_EINVAL;
+    }
+    p->lrows = p->ghost_top + owned + p->ghost_bot;
+    p->row0 = d->row_begin - p->ghost_top;
+    p->padl = 64;  // 512 B (fp64) of zero columns: vector alignment + left tile overhang
+    p->pitch = ((p->padl + d->cols + 320 + 63) / 64) * 64;  // right overhang for the widest warp strip
+    const size_t bytes = p->plane_elems() * (size_t)p->elem;
+    int rc = APDE_OK;
+    if ((rc = p->u[0].alloc(bytes)) || (rc = p->u[1].alloc(bytes)) ||
+        (d->has_source && (rc = p->src.alloc(bytes))) ||
+        (d->has_noise && ((rc = p->gh.alloc(bytes)) || (rc = p->gv.alloc(bytes)))) ||
+        (rc = p->scratch.alloc(64))) {
+        delete p;
+        return rc;
+    }
+    cudaError_t e = cudaMemset(p->u[0].p, 0, bytes);
+    if (e == cudaSuccess) e = cudaMemset(p->u[1].p, 0, bytes);
+    if (e == cudaSuccess && d->has_source) e = cudaMemset(p->src.p, 0, bytes);
+    if (e == cudaSuccess && d->has_noise) e = cudaMemset(p->gh.p, 0, bytes);
+    if (e == cudaSuccess && d->has_noise) e = cudaMemset(p->gv.p, 0, bytes);
+    if (e != cudaSuccess) {
+        set_error("plan_create: cudaMemset failed: %s", cudaGetErrorString(e));
+        delete p;
+        return APDE_ECUDA;
+    }
+    if ((rc = plan_ensure_resid(p, 4096))) {
+        delete p;
+        return rc;
+    }
+    *out = p;
+    return APDE_OK;
+}
+
+int plan_ensure_resid(apde_plan *p, int64_t cap) {
+    if (cap <= p->resid_cap) return APDE_OK;
+    DevBuf nb;
+    APDE_TRY(nb.alloc((size_t)cap * p->elem));
+    APDE_CUDA(cudaMemset(nb.p, 0, (size_t)cap * p->elem));
+    if (p->resid.p && p->resid_cap > 0)
+        APDE_CUDA(cudaMemcpy(nb.p, p->resid.p, (size_t)p->resid_cap * p->elem, cudaMemcpyDeviceToDevice));
+    std::swap(p->resid.p, nb.p);
+    std::swap(p->resid.bytes, nb.bytes);
+    p->resid_cap = cap;
+    return APDE_OK;
+}
+
+template <typename T>
+static int upload_t(apde_plan *p, const double *grid, const double *nh, const double *nv,
+                    const double *src) {
+    const Geo g = make_geo(p);
+    const int64_t grows = p->d.grows, cols = p->d.cols;
+    // stage only the rows this strip needs
+    const int64_t r0 = p->row0, r1 = p->row0 + p->lrows;  // global rows [r0, r1)
+    DevBuf stage;
+    APDE_TRY(stage.alloc((size_t)(r1 - r0) * cols * 8));
+    const int tb = 256, tg = p->sm_count * 8;
+    APDE_CUDA(cudaMemcpy(stage.p, grid + (size_t)r0 * cols, (size_t)(r1 - r0) * cols * 8, cudaMemcpyHostToDevice));
+    pack_kernel<T, false><<<tg, tb>>>(stage.as<double>(), r1 - r0, cols, r0, p->u[0].as<T>(), g);
+    if (p->d.has_source) {
+        if (!src) {
+            set_error("plan_upload: plan has_source but source is NULL");
+            return APDE_EINVAL;
+        }
+        APDE_CUDA(cudaMemcpy(stage.p, src + (size_t)r0 * cols, (size_t)(r1 - r0) * cols * 8, cudaMemcpyHostToDevice));
+        pack_kernel<T, false><<<tg, tb>>>(stage.as<double>(), r1 - r0, cols, r0, p->src.as<T>(), g);
+    }
+    if (p->d.has_noise) {
+        if (!nh || !nv) {
+            set_error("plan_upload: plan has_noise but noise_h/noise_v is NULL");
+            return APDE_EINVAL;
+        }
+        if (cols > 1) {
+            APDE_CUDA(cudaMemcpy(stage.p, nh + (size_t)r0 * (cols - 1), (size_t)(r1 - r0) * (cols - 1) * 8, cudaMemcpyHostToDevice));
+            pack_kernel<T, true><<<tg, tb>>>(stage.as<double>(), r1 - r0, cols - 1, r0, p->gh.as<T>(), g);
+        }
+        const int64_t v1 = std::min<int64_t>(r1, grows - 1);  // noise_v has grows-1 rows
+        if (v1 > r0) {
+            APDE_CUDA(cudaMemcpy(stage.p, nv + (size_t)r0 * cols, (size_t)(v1 - r0) * cols * 8, cudaMemcpyHostToDevice));
+            pack_kernel<T, true><<<tg, tb>>>(stage.as<double>(), v1 - r0, cols, r0, p->gv.as<T>(), g);
+        }
+    }
+    APDE_CUDA(cudaGetLastError());
+    APDE_CUDA(cudaMemcpy(p->u[1].p, p->u[0].p, p->plane_elems() * sizeof(T), cudaMemcpyDeviceToDevice));
+    APDE_CUDA(cudaDeviceSynchronize());
+    p->cur = 0;
+    p->filled = true;
+    p->launches += 1 + (p->d.has_source ? 1 : 0) + (p->d.has_noise ? 2 : 0);
+    return APDE_OK;
+}
+
+int plan_upload(apde_plan *p, const double *grid, const double *nh, const double *nv, const double *src) {
+    if (!p || !grid) {
+        set_error("plan_upload: NULL argument");
+        return APDE_EINVAL;
+    }
+    APDE_CUDA(cudaSetDevice(p->device));
+    return p->elem == 8 ? upload_t<double>(p, grid, nh, nv, src) : upload_t<float>(p, grid, nh, nv, src);
+}
+
+template <typename T> static int fill_t(apde_plan *p, const apde_fill_desc *f) {
+    const Geo g = make_geo(p);
+    fill_kernel<T><<<p->sm_count * 8, 256>>>(p->u[0].as<T>(), p->d.has_source ? p->src.as<T>() : nullptr,
+                                             p->d.has_noise ? p->gh.as<T>() : nullptr,
+                                             p->d.has_noise ? p->gv.as<T>() : nullptr, g, *f);
+    APDE_CUDA(cudaGetLastError());
+    APDE_CUDA(cudaMemcpy(p->u[1].p, p->u[0].p, p->plane_elems() * sizeof(T), cudaMemcpyDeviceToDevice));
+    APDE_CUDA(cudaDeviceSynchronize());
+    p->cur = 0;
+    p->filled = true;
+    p->launches += 1;
+    return APDE_OK;
+}
+
+int plan_fill(apde_plan *p, const apde_fill_desc *f) {
+    if (!p || !f) {
+        set_error("plan_fill: NULL argument");
+        return APDE_EINVAL;
+    }
+    APDE_CUDA(cudaSetDevice(p->device));
+    return p->elem == 8 ? fill_t<double>(p, f) : fill_t<float>(p, f);
+}
+
+int plan_download(apde_plan *p, double *grid) {
+    if (!p || !grid) {
+        set_error("plan_download: NULL argument");
+        return APDE_EINVAL;
+    }
+    APDE_CUDA(cudaSetDevice(p->device));
+    const Geo g = make_geo(p);
+    const int64_t owned = g.own_hi - g.own_lo;
+    DevBuf stage;
+    APDE_TRY(stage.alloc((size_t)owned * g.cols * 8));
+    const int64_t out_row0 = p->d.row_begin;
+    if (p->elem == 8)
+        unpack_kernel<double><<<p->sm_count * 8, 256>>>(p->u[p->cur].as<double>(), g, stage.as<double>(), out_row0, owned);
+    else
+        unpack_kernel<float><<<p->sm_count * 8, 256>>>(p->u[p->cur].as<float>(), g, stage.as<double>(), out_row0, owned);
+    APDE_CUDA(cudaGetLastError());
+    APDE_CUDA(cudaMemcpy(grid + (size_t)out_row0 * g.cols, stage.p, (size_t)owned * g.cols * 8, cudaMemcpyDeviceToHost));
+    p->launches += 1;
+    return APDE_OK;
+}
+
+// ---- v0 driver ---------------------------------------------------------------------------
+template <typename T, bool NOISE, bool SRC>
+static int run_v0(apde_plan *p, int64_t n_sweeps, int64_t sweep_base, cudaStream_t st) {
+    const Geo g = make_geo(p);
+    const long long hw = (g.cols - 1) / 2;
+    if (hw < 1 || g.lrows < 3) return APDE_OK;
+    dim3 block(256);
+    dim3 grid((unsigned)((hw + 255) / 256), (unsigned)std::min<long long>(g.lrows - 2, 32768));
+    T *u = p->u[p->cur].as<T>();
+    for (int64_t s = 0; s < n_sweeps; ++s) {
+        T *slot = p->resid.as<T>() + sweep_base + s;
+        for (int colour = 0; colour < 2; ++colour) {
+            rb_colour_kernel<T, NOISE, SRC><<<grid, block, 0, st>>>(u, p->src.as<T>(), p->gh.as<T>(),
+                                                                  p->gv.as<T>(), g, colour, slot);
+            p->launches++;
+        }
+    }
+    APDE_CUDA(cudaGetLastError());
+    return APDE_OK;
+}
+
+template <typename T>
+static int run_dispatch(apde_plan *p, int64_t n, int64_t base, int phase, cudaStream_t st) {
+    if (phase == 2) return APDE_OK;  // v0 does everything in phase 0/1
+    const bool N = p->d.has_noise, S = p->d.has_source;
+    if (N && S) return run_v0<T, true, true>(p, n, base, st);
+    if (N) return run_v0<T, true, false>(p, n, base, st);
+    if (S) return run_v0<T, false, true>(p, n, base, st);
+    return run_v0<T, false, false>(p, n, base, st);
+}
+
+int plan_run(apde_plan *p, int64_t n_sweeps, int64_t sweep_base, int phase, cudaStream_t st) {
+    if (!p || n_sweeps < 0 || sweep_base < 0 || phase < 0 || phase > 2) {
+        set_error("plan_run: bad argument");
+        return APDE_EINVAL;
+    }
+    if (!p->filled) {
+        set_error("plan_run: plan has no data (call apde_plan_upload or apde_plan_fill first)");
+        return APDE_ESTATE;
+    }
+    if ((p->ghost_top || p->ghost_bot) && n_sweeps > p->d.temporal_depth) {
+        set_error("plan_run: %lld sweeps between halo exchanges exceeds temporal_depth %d",
+                  (long long)n_sweeps, p->d.temporal_depth);
+        return APDE_EINVAL;
+    }
+    APDE_CUDA(cudaSetDevice(p->device));
+    if (sweep_base + n_sweeps > p->resid_cap) {
+        // growing reallocates: make sure nothing in flight still writes the old array
+        APDE_CUDA(cudaDeviceSynchronize());
+        APDE_TRY(plan_ensure_resid(p, std::max<int64_t>(2 * p->resid_cap, sweep_base + n_sweeps)));
+    }
+    if (phase != 2 && n_sweeps > 0)
+        APDE_CUDA(cudaMemsetAsync((char *)p->resid.p + (size_t)sweep_base * p->elem, 0, (size_t)n_sweeps * p->elem, st));
+    return p->elem == 8 ? run_dispatch<double>(p, n_sweeps, sweep_base, phase, st)
+                        : run_dispatch<float>(p, n_sweeps, sweep_base, phase, st);
+}
+
+int plan_halo(apde_plan *p, int side, void **send_ptr, void **recv_ptr, int64_t *nbytes) {
+    if (!p || side < 0 || side > 1 || !send_ptr || !recv_ptr || !nbytes) {
+        set_error("plan_halo: bad argument");
+        return APDE_EINVAL;
+    }
+    char *base = (char *)p->u[p->cur].p;
+    const size_t rowb = (size_t)p->pitch * p->elem;
+    *nbytes = (int64_t)(p->halo * rowb);
+    *send_ptr = *recv_ptr = nullptr;
+    if (side == 0 && p->ghost_top) {
+        *recv_ptr = base;                                  // ghost rows [0, halo)
+        *send_ptr = base + (size_t)p->ghost_top * rowb;    // first `halo` owned rows
+    } else if (side == 1 && p->ghost_bot) {
+        const int64_t own_hi = p->lrows - p->ghost_bot;
+        *recv_ptr = base + (size_t)own_hi * rowb;          // ghost rows below
+        *send_ptr = base + (size_t)(own_hi - p->halo) * rowb;  // last `halo` owned rows
+    }
+    return APDE_OK;
+}
+
+int plan_read_residuals(apde_plan *p, int64_t first, int64_t count, double *out, cudaStream_t st) {
+    if (!p || first < 0 || count < 0 || first + count > p->resid_cap || (!out && count)) {
+        set_error("plan_read_residuals: bad range");
+        return APDE_EINVAL;
+    }
+    if (count == 0) return APDE_OK;
+    APDE_CUDA(cudaSetDevice(p->device));
+    if (p->elem == 8) {
+        APDE_CUDA(cudaMemcpyAsync(out, p->resid.as<double>() + first, (size_t)count * 8, cudaMemcpyDeviceToHost, st));
+        APDE_CUDA(cudaStreamSynchronize(st));
+    } else {
+        std::vector<float> tmp((size_t)count);
+        APDE_CUDA(cudaMemcpyAsync(tmp.data(), p->resid.as<float>() + first, (size_t)count * 4, cudaMemcpyDeviceToHost, st));
+        APDE_CUDA(cudaStreamSynchronize(st));
+        for (int64_t k = 0; k < count; ++k) out[k] = (double)tmp[(size_t)k];
+    }
+    return APDE_OK;
+}
+
+int plan_checksum(apde_plan *p, double *sum_out, double *absmax_out, cudaStream_t st) {
+    if (!p) {
+        set_error("plan_checksum: NULL plan");
+        return APDE_EINVAL;
+    }
+    APDE_CUDA(cudaSetDevice(p->device));
+    const Geo g = make_geo(p);
+    APDE_CUDA(cudaMemsetAsync(p->scratch.p, 0, 16, st));
+    if (p->elem == 8)
+        checksum_kernel<double><<<p->sm_count * 4, 256, 0, st>>>(p->u[p->cur].as<double>(), g, p->scratch.as<double>());
+    else
+        checksum_kernel<float><<<p->sm_count * 4, 256, 0, st>>>(p->u[p->cur].as<float>(), g, p->scratch.as<double>());
+    APDE_CUDA(cudaGetLastError());
+    p->launches++;
+    double h[2];
+    APDE_CUDA(cudaMemcpyAsync(h, p->scratch.p, 16, cudaMemcpyDeviceToHost, st));
+    APDE_CUDA(cudaStreamSynchronize(st));
+    if (sum_out) *sum_out = h[0];
+    if (absmax_out) *absmax_out = h[1];
+    return APDE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// one-shot host-buffer solve
+// ------------------------------------------------------------------------------------------
+int solve_redblack(int elem, double *grid, const double *nh, const double *nv, const double *src,
+                   int64_t rows, int64_t cols, double tol, int64_t max_iter, int check_every,
+                   int temporal_depth, double *hist, int64_t *iters, double *ksec) {
+    if (ksec) *ksec = 0.0;
+    if (max_iter <= 0) {
+        *iters = max_iter;
+        return APDE_OK;
+    }
+    if (check_every <= 0) check_every = 32;
+    if (temporal_depth <= 0) temporal_depth = 4;
+    if (rows < 3 || cols < 3) {
+        const int64_t n = (0.0 < tol) ? std::min<int64_t>(check_every, max_iter) : max_iter;
+        for (int64_t k = 0; k < n; ++k) hist[k] = 0.0;
+        *iters = n;
+        return APDE_OK;
+    }
+    apde_plan_desc d{};
+    d.dtype_bytes = elem;
+    d.has_noise = (nh != nullptr);
+    d.has_source = (src != nullptr);
+    d.temporal_depth = temporal_depth;
+    d.grows = rows;
+    d.cols = cols;
+    d.row_begin = 0;
+    d.row_end = rows;
+    apde_plan *p = nullptr;
+    APDE_TRY(plan_create(&p, &d));
+    struct Guard {
+        apde_plan *p;
+        ~Guard() { delete p; }
+    } guard{p};
+    APDE_TRY(plan_upload(p, grid, nh, nv, src));
+    EventPair ev;
+    APDE_TRY(ev.init());
+    float total_ms = 0.f;
+    int64_t done = 0;
+    bool stop = false;
+    while (done < max_iter && !stop) {
+        const int64_t n = std::min<int64_t>(check_every, max_iter - done);
+        APDE_CUDA(cudaEventRecord(ev.a));
+        APDE_TRY(plan_run(p, n, done, 0, 0));
+        APDE_CUDA(cudaEventRecord(ev.b));
+        APDE_TRY(plan_read_residuals(p, done, n, hist + done, 0));
+        float ms = 0.f;
+        APDE_CUDA(cudaEventElapsedTime(&ms, ev.a, ev.b));
+        total_ms += ms;
+        for (int64_t k = 0; k < n; ++k)
+            if (hist[done + k] < tol) stop = true;  // solver.py:283 tested every check_every sweeps
+        done += n;
+    }
+    *iters = done;
+    if (ksec) *ksec = total_ms * 1e-3;
+    return plan_download(p, grid);
+}
+
+}  // namespace apde

@@ -1,0 +1,154 @@
+/*
+ * apde.h -- C-ABI of libapde.so, the B200 (sm_100a) backend for the relaxation hot
+ * path of danieleschmidt/analog-pde-solver-sim.
+ *
+ * The reference has no FFI: its hot path is a pure-Python triple loop inside
+ *   AnalogPDESolver.solve   analog_pde_solver/solver.py:262-287
+ *   DigitalSolver.solve     analog_pde_solver/solver.py:344-368
+ * so this boundary is what a maintainer would bind with ctypes from those two
+ * methods (INTEGRATION.md shows the stub).  Plain pointers and sizes only.
+ *
+ * Conventions
+ *   - every function returns 0 (APDE_OK) or a negative APDE_E* code;
+ *     apde_last_error() gives the thread-local message of the last failure.
+ *   - there is NO CPU fallback: without a usable sm_100 device the solve
+ *     functions fail with APDE_ENODEV.
+ *   - host arrays are C-order float64 exactly as the reference holds them:
+ *       grid    rows*cols        boundary ring + initial guess in, solution out   (solver.py:250-251, :289)
+ *       noise_h rows*(cols-1)    AnalogPDESolver._noise_h (solver.py:209) or NULL (=> 1.0, DigitalSolver)
+ *       noise_v (rows-1)*cols    AnalogPDESolver._noise_v (solver.py:210) or NULL
+ *       source  rows*cols        h^2 * f (solver.py:253-259) or NULL (=> Laplace)
+ *       residual_history  capacity max_iter doubles, one max_change per sweep     (solver.py:281)
+ *       iterations_run    number of sweeps executed                               (solver.py:283-287)
+ */
+#ifndef APDE_H
+#define APDE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APDE_VERSION 100 /* 1.0.0, tracks the reference's __version__ (analog_pde_solver/__init__.py:11) */
+
+enum {
+    APDE_OK = 0,
+    APDE_EINVAL = -1,  /* bad shape / NULL pointer / bad option */
+    APDE_ENODEV = -2,  /* no CUDA device of compute capability 10.x */
+    APDE_ECUDA = -3,   /* CUDA runtime error (message in apde_last_error) */
+    APDE_ENOMEM = -4,  /* device or host allocation failed */
+    APDE_ESTATE = -5   /* plan used in the wrong state */
+};
+
+int apde_version(void);
+int apde_device_count(void);           /* number of sm_100 devices visible, 0 if none */
+const char *apde_last_error(void);     /* thread-local, valid until the next call on this thread */
+
+/* ------------------------------------------------------------------------------------------
+ * EXACT path -- replaces the sweep loops solver.py:263-287 and :344-368 bit for bit.
+ * Anti-diagonal wavefront lexicographic Gauss-Seidel, fp64, compiled -fmad=false.  Stops at the
+ * first sweep whose max_change < tol (strict) like solver.py:283-285; tol <= 0 runs max_iter sweeps.
+ * kernel_seconds (optional) = device time of the relaxation kernels only.
+ * ---------------------------------------------------------------------------------------- */
+int apde_solve_exact_f64(double *grid, const double *noise_h, const double *noise_v,
+                         const double *source, int64_t rows, int64_t cols, double tol,
+                         int64_t max_iter, double *residual_history, int64_t *iterations_run,
+                         double *kernel_seconds);
+/* Same, choosing the kernel: path 0 = automatic, 1 = one-CTA shared-memory kernel (fails with
+ * APDE_EINVAL if the problem does not fit), 2 = multi-CTA ring kernel.  Results are identical. */
+int apde_solve_exact_f64_path(double *grid, const double *noise_h, const double *noise_v,
+                              const double *source, int64_t rows, int64_t cols, double tol,
+                              int64_t max_iter, double *residual_history, int64_t *iterations_run,
+                              double *kernel_seconds, int path);
+
+/* ------------------------------------------------------------------------------------------
+ * THROUGHPUT path -- red-black Gauss-Seidel (colour (i+j) even first), conductances g = 1/noise
+ * precomputed on the device, `temporal_depth` sweeps fused per pass over HBM.  Same fixed point as
+ * the reference; iterates differ (different update order), so iterations_run may differ by a few
+ * sweeps.  Convergence is tested every `check_every` sweeps: iterations_run is a multiple of
+ * check_every (or max_iter) and residual_history holds every executed sweep.
+ *   _f64: fp64 arithmetic;  _f32: fp32 arithmetic (host arrays stay float64, converted on device).
+ * check_every <= 0 => 32; temporal_depth <= 0 => library default.
+ * ---------------------------------------------------------------------------------------- */
+int apde_solve_redblack_f64(double *grid, const double *noise_h, const double *noise_v,
+                            const double *source, int64_t rows, int64_t cols, double tol,
+                            int64_t max_iter, int check_every, int temporal_depth,
+                            double *residual_history, int64_t *iterations_run,
+                            double *kernel_seconds);
+int apde_solve_redblack_f32(double *grid, const double *noise_h, const double *noise_v,
+                            const double *source, int64_t rows, int64_t cols, double tol,
+                            int64_t max_iter, int check_every, int temporal_depth,
+                            double *residual_history, int64_t *iterations_run,
+                            double *kernel_seconds);
+
+/* ------------------------------------------------------------------------------------------
+ * Device-resident strip plans (benchmark scale and multi-GPU row strips).
+ *
+ * A plan owns one row strip of a global grows x cols problem on the CURRENT CUDA device:
+ * global rows [row_begin, row_end) plus `halo` ghost rows on each interior side.  Nothing O(N^2)
+ * has to cross PCIe: inputs can be generated on the device.  One process per GPU drives one plan;
+ * the host (torch.distributed / NCCL) moves the halo rows between plans using the device
+ * pointers returned by apde_plan_halo().
+ * ---------------------------------------------------------------------------------------- */
+typedef struct apde_plan apde_plan;
+
+typedef struct {
+    int32_t dtype_bytes;    /* 8 = fp64, 4 = fp32 */
+    int32_t has_noise;      /* per-link conductances present */
+    int32_t has_source;     /* Poisson source present */
+    int32_t temporal_depth; /* max sweeps fused per pass (>=1); halo = 2*temporal_depth rows */
+    int64_t grows, cols;    /* global grid */
+    int64_t row_begin;      /* first owned global row */
+    int64_t row_end;        /* one past last owned global row */
+} apde_plan_desc;
+
+typedef struct {
+    int32_t kind;           /* 0 = zeros; 1 = sin source  h^2 * (-2 pi^2 sin(pi x) sin(pi y)),
+                               x = i/(grows-1), y = j/(cols-1), h = 1/(max(grows,cols)-1)
+                               (tests/test_solver.py:28-32 + solver.py:254-259) */
+    int32_t top_hot;        /* 1 => global row 0 = 1.0 (examples/laplace_heat_demo.py:32-38), else zero ring */
+    double noise_level;     /* sigma of the multiplicative link mismatch 1 + sigma*N(0,1) */
+    uint64_t seed;          /* counter-based Philox4x32-10 key; link id = counter (NOT numpy's PCG64 stream) */
+} apde_fill_desc;
+
+int apde_plan_create(apde_plan **plan, const apde_plan_desc *desc);
+int apde_plan_destroy(apde_plan *plan);
+
+/* Upload host float64 arrays covering the GLOBAL grid (only this strip's rows are read). */
+int apde_plan_upload(apde_plan *plan, const double *grid, const double *noise_h,
+                     const double *noise_v, const double *source);
+/* Generate inputs on the device. */
+int apde_plan_fill(apde_plan *plan, const apde_fill_desc *fill);
+/* Copy this strip's owned rows into a GLOBAL host float64 grid. */
+int apde_plan_download(apde_plan *plan, double *grid);
+
+/* Run n_sweeps red-black sweeps on `stream` (a cudaStream_t passed as void*, NULL = default),
+ * fusing up to `temporal_depth` sweeps per pass.  n_sweeps must be <= the plan's temporal_depth
+ * when the strip has neighbours (halo validity); single-strip plans accept any n_sweeps.
+ * `phase`: 0 = whole strip, 1 = only the row blocks adjacent to neighbours (launch first, then
+ * start the halo exchange), 2 = the remaining interior blocks.  Per-sweep max_change goes to the
+ * device residual array at index sweep_base + s.  Asynchronous. */
+int apde_plan_run(apde_plan *plan, int64_t n_sweeps, int64_t sweep_base, int phase, void *stream);
+
+/* After a group of sweeps: device pointers + byte counts of the rows to send to / receive from the
+ * upper (side 0) and lower (side 1) neighbour.  Pointers are NULL on a side with no neighbour. */
+int apde_plan_halo(apde_plan *plan, int side, void **send_ptr, void **recv_ptr, int64_t *nbytes);
+
+/* Device pointer of the per-sweep max_change array (plan dtype) and its capacity. */
+int apde_plan_residuals(apde_plan *plan, void **dev_ptr, int64_t *capacity);
+/* Copy residuals [first, first+count) to host as float64 (synchronises `stream`). */
+int apde_plan_read_residuals(apde_plan *plan, int64_t first, int64_t count, double *out, void *stream);
+/* Kernels launched by this plan since creation (bench.py's gpu_launches). */
+int64_t apde_plan_launch_count(const apde_plan *plan);
+/* sum_j u[row, j] style checksum of owned rows (fp64 accumulate) for cheap cross-rank checks. */
+int apde_plan_checksum(apde_plan *plan, double *sum_out, double *abs_max_out, void *stream);
+
+/* Device-to-device copy on `stream` (same device or peer device, e.g. a neighbour strip's halo
+ * rows when both plans live in one process).  Asynchronous. */
+int apde_memcpy_dtod(void *dst, const void *src, int64_t nbytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APDE_H */

@@ -1,0 +1,157 @@
+"""ctypes front-end of the CPU oracle (oracle/apde_oracle.c).  TEST INFRASTRUCTURE ONLY.
+
+Parity status: pinned -- see the header of apde_oracle.c and tests/test_oracle.py.
+Every function mirrors a piece of the reference's hot path
+(analog_pde_solver/solver.py:262-287, :344-368 upstream).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from typing import Optional, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libapde_oracle.so")
+_lib = None
+
+_dp = ctypes.POINTER(ctypes.c_double)
+_fp = ctypes.POINTER(ctypes.c_float)
+_i64 = ctypes.c_int64
+
+
+def build(force: bool = False) -> str:
+    """Compile the C restatement with gcc (idempotent)."""
+    src = os.path.join(_HERE, "apde_oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "-B", "libapde_oracle.so"], check=True,
+                       stdout=subprocess.DEVNULL, env={**os.environ, "CC": "gcc"})
+    return _LIB_PATH
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        lib = ctypes.CDLL(_LIB_PATH)
+        lib.apde_oracle_gs_f64.restype = _i64
+        lib.apde_oracle_gs_f64.argtypes = [_dp, _dp, _dp, _dp, _i64, _i64, ctypes.c_double, _i64, _dp]
+        lib.apde_oracle_gs_f64_mt.restype = _i64
+        lib.apde_oracle_gs_f64_mt.argtypes = [_dp, _dp, _dp, _dp, _i64, _i64, _i64, _dp, ctypes.c_int]
+        lib.apde_oracle_rb_f64.restype = _i64
+        lib.apde_oracle_rb_f64.argtypes = [_dp, _dp, _dp, _dp, _i64, _i64, _i64, _dp]
+        lib.apde_oracle_rb_f32.restype = _i64
+        lib.apde_oracle_rb_f32.argtypes = [_fp, _fp, _fp, _fp, _i64, _i64, _i64, _fp]
+        lib.apde_oracle_recip_f64.restype = None
+        lib.apde_oracle_recip_f64.argtypes = [_dp, _dp, _i64]
+        lib.apde_oracle_recip_f32.restype = None
+        lib.apde_oracle_recip_f32.argtypes = [_dp, _fp, _i64]
+        lib.apde_oracle_max_threads.restype = ctypes.c_int
+        _lib = lib
+    return _lib
+
+
+def _ptr(a: Optional[np.ndarray], ct):
+    if a is None:
+        return ctypes.cast(None, ct)
+    return a.ctypes.data_as(ct)
+
+
+def _chk(a, shape, dtype, name):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=dtype)
+    if a.shape != shape:
+        raise ValueError(f"{name}: expected shape {shape}, got {a.shape}")
+    return a
+
+
+def max_threads() -> int:
+    return int(_load().apde_oracle_max_threads())
+
+
+def gauss_seidel(grid: np.ndarray, noise_h=None, noise_v=None, source=None,
+                 tol: float = 1e-6, max_iter: int = 10_000) -> Tuple[np.ndarray, np.ndarray, int]:
+    """Lexicographic Gauss-Seidel exactly as solver.py:262-287 / :344-368.
+
+    `grid` holds the Dirichlet ring + initial guess (solver.py:250-251).  Returns
+    (solution, residual_history, iterations_run).  The input is not modified.
+    """
+    lib = _load()
+    u = np.array(grid, dtype=np.float64, order="C", copy=True)
+    rows, cols = u.shape
+    nh = _chk(noise_h, (rows, cols - 1), np.float64, "noise_h")
+    nv = _chk(noise_v, (rows - 1, cols), np.float64, "noise_v")
+    src = _chk(source, (rows, cols), np.float64, "source")
+    hist = np.zeros(max(int(max_iter), 1), dtype=np.float64)
+    n = lib.apde_oracle_gs_f64(_ptr(u, _dp), _ptr(nh, _dp), _ptr(nv, _dp), _ptr(src, _dp),
+                               rows, cols, float(tol), int(max_iter), _ptr(hist, _dp))
+    return u, hist[:n].copy(), int(n)
+
+
+def gauss_seidel_mt(grid, noise_h=None, noise_v=None, source=None, n_sweeps: int = 1,
+                    n_threads: int = 0):
+    """Column-block pipelined multi-thread variant; bitwise equal to gauss_seidel(tol=0)."""
+    lib = _load()
+    u = np.array(grid, dtype=np.float64, order="C", copy=True)
+    rows, cols = u.shape
+    nh = _chk(noise_h, (rows, cols - 1), np.float64, "noise_h")
+    nv = _chk(noise_v, (rows - 1, cols), np.float64, "noise_v")
+    src = _chk(source, (rows, cols), np.float64, "source")
+    hist = np.zeros(max(int(n_sweeps), 1), dtype=np.float64)
+    if n_threads <= 0:
+        n_threads = max_threads()
+    lib.apde_oracle_gs_f64_mt(_ptr(u, _dp), _ptr(nh, _dp), _ptr(nv, _dp), _ptr(src, _dp),
+                              rows, cols, int(n_sweeps), _ptr(hist, _dp), int(n_threads))
+    return u, hist[:n_sweeps].copy(), int(n_sweeps)
+
+
+def reciprocal_links(noise: np.ndarray, dtype) -> np.ndarray:
+    """g = 1/noise in fp64, rounded once to `dtype` (what kernel K5 computes)."""
+    lib = _load()
+    noise = np.ascontiguousarray(noise, dtype=np.float64)
+    out = np.empty(noise.shape, dtype=dtype)
+    if np.dtype(dtype) == np.float64:
+        lib.apde_oracle_recip_f64(_ptr(noise, _dp), _ptr(out, _dp), noise.size)
+    else:
+        lib.apde_oracle_recip_f32(_ptr(noise, _dp), _ptr(out, _fp), noise.size)
+    return out
+
+
+def red_black(grid, noise_h=None, noise_v=None, source=None, n_sweeps: int = 1,
+              dtype=np.float64):
+    """Red-black Gauss-Seidel, colour (i+j) even first, fixed sweep count.
+
+    The CPU statement of the CUDA throughput kernels' arithmetic (expression tree
+    documented in apde_oracle.c).  Host-side inputs are fp64 like the C-ABI's; the
+    working type is `dtype`.  Returns (grid in `dtype`, hist in `dtype`, n_sweeps).
+    """
+    lib = _load()
+    dtype = np.dtype(dtype)
+    u = np.array(grid, dtype=np.float64, order="C", copy=True).astype(dtype)
+    rows, cols = u.shape
+    if (noise_h is None) != (noise_v is None):
+        raise ValueError("noise_h and noise_v must be given together")
+    gh = gv = None
+    if noise_h is not None:
+        gh = reciprocal_links(_chk(noise_h, (rows, cols - 1), np.float64, "noise_h"), dtype)
+        gv = reciprocal_links(_chk(noise_v, (rows - 1, cols), np.float64, "noise_v"), dtype)
+    src = None
+    if source is not None:
+        src = _chk(source, (rows, cols), np.float64, "source").astype(dtype)
+    hist = np.zeros(max(int(n_sweeps), 1), dtype=dtype)
+    if dtype == np.float64:
+        lib.apde_oracle_rb_f64(_ptr(u, _dp), _ptr(gh, _dp), _ptr(gv, _dp), _ptr(src, _dp),
+                               rows, cols, int(n_sweeps), _ptr(hist, _dp))
+    elif dtype == np.float32:
+        lib.apde_oracle_rb_f32(_ptr(u, _fp), _ptr(gh, _fp), _ptr(gv, _fp), _ptr(src, _fp),
+                               rows, cols, int(n_sweeps), _ptr(hist, _fp))
+    else:
+        raise ValueError("dtype must be float32 or float64")
+    return u, hist[:n_sweeps].copy(), int(n_sweeps)
+
+
+__all__ = ["build", "gauss_seidel", "gauss_seidel_mt", "red_black", "reciprocal_links", "max_threads"]

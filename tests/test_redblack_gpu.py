@@ -1,0 +1,130 @@
+"""GPU: the red-black throughput path through the C-ABI.
+
+Parity contract: (1) at a fixed sweep count the CUDA kernels equal the red-black
+CPU oracle bit for bit (fp64 and fp32, every kernel variant); (2) converged with tol ~ 1e-13 the
+fp64 result is within 1e-10 (relative, max-norm) of the reference's lexicographic answer on SPD
+cases; fp32 within 1e-5 on a small converged case."""
+import numpy as np
+import pytest
+
+import oracle
+from helpers import random_problem, top_hot, zero_boundary, sin_source
+from analog_pde_solver import AnalogPDESolver, DigitalSolver, _backend
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(3, 3), (4, 5), (5, 4), (17, 33), (64, 64), (65, 130), (130, 67), (257, 300), (200, 1031)]
+
+
+@pytest.mark.parametrize("rows,cols", SHAPES)
+@pytest.mark.parametrize("sigma,src", [(0.0, False), (0.0, True), (0.01, False), (0.02, True)])
+@pytest.mark.parametrize("mode,dt", [("redblack", np.float64), ("redblack32", np.float32)])
+@pytest.mark.parametrize("depth", [1, 2, 3, 4])
+def test_fixed_sweeps_bit_exact_vs_rb_oracle(rows, cols, sigma, src, mode, dt, depth):
+    k = 9
+    g0, nh, nv, s = random_problem(rows, cols, sigma, seed=rows * 131 + cols, with_source=src)
+    ru, rh, _ = oracle.red_black(g0, nh, nv, s, k, dtype=dt)
+    g = g0.copy()
+    hist, n, _ = _backend.solve(mode, g, nh, nv, s, 0.0, k, check_every=4, temporal_depth=depth)
+    assert n == k
+    assert hist.astype(dt).tobytes() == rh.tobytes()
+    assert g.astype(dt).tobytes() == ru.tobytes()
+
+
+def test_converged_fp64_within_1e10_of_reference_answer():
+    """tol = 1e-13 on SPD cases: |u_rb - u_lex| <= 1e-10 * |u|  (north_star tolerance, fp64)."""
+    for rows, cols, sigma, seed in [(20, 20, 0.0, 1), (20, 20, 0.01, 0), (64, 64, 0.01, 0), (48, 30, 0.0, 2)]:
+        g0, nh, nv, s = random_problem(rows, cols, sigma, seed)
+        ref, _, rn = oracle.gauss_seidel(g0, nh, nv, s, 1e-13, 200000)
+        g = g0.copy()
+        hist, n, _ = _backend.solve("redblack", g, nh, nv, s, 1e-13, 200000, check_every=32)
+        assert n < 200000 and n % 32 == 0
+        assert hist[-32:].min() < 1e-13
+        assert np.max(np.abs(g - ref)) <= 1e-10 * np.max(np.abs(ref))
+
+
+def test_converged_fp32_within_1e5_on_small_grid():
+    """fp32 bar: <= 1e-5 relative on a converged small grid (it stagnates above N ~ 48)."""
+    g0, nh, nv, s = random_problem(24, 24, 0.01, 4)
+    ref, _, _ = oracle.gauss_seidel(g0, nh, nv, s, 1e-13, 200000)
+    g = g0.copy()
+    hist, n, _ = _backend.solve("redblack32", g, nh, nv, s, 1e-7, 20000, check_every=32)
+    assert np.max(np.abs(g - ref)) <= 1e-5 * np.max(np.abs(ref))
+
+
+def test_python_classes_redblack_mode():
+    a = AnalogPDESolver(rows=20, cols=20, noise_level=0.01, rng_seed=0)
+    ref = AnalogPDESolver(rows=20, cols=20, noise_level=0.01, rng_seed=0)
+    u = a.solve(top_hot, tol=1e-6, max_iter=20000, mode="redblack")
+    r = ref.solve(top_hot, tol=1e-6, max_iter=20000)  # exact path
+    assert a.iterations_run % 32 == 0 and 0 < a.iterations_run - ref.iterations_run < 64
+    assert len(a.residual_history) == a.iterations_run
+    assert np.max(np.abs(u - r)) < 1e-4
+    d = DigitalSolver(rows=15, cols=15)
+    d.backend_mode = "redblack32"
+    ud = d.solve(zero_boundary, source_fn=sin_source, tol=1e-6)
+    exact = np.array([[np.sin(np.pi * i / 14) * np.sin(np.pi * j / 14) for j in range(15)] for i in range(15)])
+    assert np.max(np.abs(ud - exact)) < 0.05 and d.wall_time_s > 0
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("noise", [0.0, 0.01])
+def test_plan_device_fill_matches_host_statement(dt, noise):
+    """apde_plan_fill: zero ring / top_hot, sin source (tests/test_solver.py:28-32 upstream scaled by
+    h^2, solver.py:254-259) generated on the device; iterate parity vs the oracle fed the
+    downloaded inputs is covered by building the same arrays on the host here."""
+    rows, cols = 96, 72
+    with _backend.Plan(rows, cols, dtype=dt, has_noise=noise > 0, has_source=True, temporal_depth=2) as p:
+        p.fill(kind=1, top_hot=True, noise_level=noise, seed=11)
+        u0 = p.download()
+        assert (u0[0] == 1.0).all() and (u0[1:] == 0.0).all()
+        p.run(6, 0)
+        hist = p.residuals(0, 6)
+        u = p.download()
+    h = 1.0 / (max(rows, cols) - 1)
+    ii, jj = np.meshgrid(np.arange(rows), np.arange(cols), indexing="ij")
+    src = h ** 2 * (-2.0 * np.pi ** 2 * np.sin(np.pi * ii / (rows - 1)) * np.sin(np.pi * jj / (cols - 1)))
+    if noise == 0:
+        ru, rh, _ = oracle.red_black(u0, None, None, src, 6, dtype=dt)
+        tol = 1e-13 if dt == np.float64 else 1e-6
+        assert np.max(np.abs(u - ru)) < tol  # device sin vs libm sin: last-ulp differences only
+        assert abs(hist[0] - rh[0]) < tol
+    else:
+        assert np.isfinite(u).all() and hist[0] > 0
+
+
+def test_plan_two_strips_equal_one_strip_bitwise():
+    """Row strips with ghost rows + halo exchange reproduce the single-strip result bit for bit
+    (same arithmetic per node).  Two plans on one GPU stand in for two ranks; the halo rows are
+    moved through host memory here, NCCL in production (analog_pde_solver/strips.py)."""
+    rows, cols, depth, groups = 150, 90, 3, 4
+    g0, nh, nv, s = random_problem(rows, cols, 0.01, seed=9)
+    lib = _backend.load()
+    for dt in (np.float64, np.float32):
+        with _backend.Plan(rows, cols, dtype=dt, has_noise=True, has_source=True, temporal_depth=depth) as whole:
+            whole.upload(g0, nh, nv, s)
+            for g in range(groups):
+                whole.run(depth, g * depth)
+            ref = whole.download()
+            ref_hist = whole.residuals(0, groups * depth)
+        split = 70
+        a = _backend.Plan(rows, cols, 0, split, dtype=dt, has_noise=True, has_source=True, temporal_depth=depth)
+        b = _backend.Plan(rows, cols, split, rows, dtype=dt, has_noise=True, has_source=True, temporal_depth=depth)
+        a.upload(g0, nh, nv, s)
+        b.upload(g0, nh, nv, s)
+        for g in range(groups):
+            a.run(depth, g * depth)
+            b.run(depth, g * depth)
+            sa, ra, n = a.halo(1)
+            sb, rb, n2 = b.halo(0)
+            assert n == n2 and a.halo(0)[0] is None and b.halo(1)[0] is None
+            _backend.check(lib.apde_memcpy_dtod(rb, sa, n, None))
+            _backend.check(lib.apde_memcpy_dtod(ra, sb, n, None))
+        out = np.zeros((rows, cols))
+        a.download(out)
+        b.download(out)
+        hist = np.maximum(a.residuals(0, groups * depth), b.residuals(0, groups * depth))
+        a.close()
+        b.close()
+        assert out.tobytes() == ref.tobytes()
+        assert hist.tobytes() == ref_hist.tobytes()
