@@ -27,7 +27,7 @@ ERROR_NAMES = {-1: "APDE_EINVAL", -2: "APDE_ENODEV", -3: "APDE_ECUDA", -4: "APDE
 EXPORTED_SYMBOLS = (
     "apde_version", "apde_device_count", "apde_last_error",
     "apde_solve_exact_f64", "apde_solve_exact_f64_path", "apde_solve_redblack_f64", "apde_solve_redblack_f32",
-    "apde_plan_create", "apde_plan_destroy", "apde_plan_upload", "apde_plan_fill",
+    "apde_plan_create", "apde_plan_destroy", "apde_plan_upload", "apde_plan_upload_rows", "apde_plan_download_rows", "apde_plan_fill",
     "apde_plan_download", "apde_plan_run", "apde_plan_halo", "apde_plan_residuals",
     "apde_plan_read_residuals", "apde_plan_launch_count", "apde_plan_checksum", "apde_memcpy_dtod",
 )
@@ -83,6 +83,10 @@ def load():
     lib.apde_plan_destroy.argtypes = [_vp]
     lib.apde_plan_upload.restype = ctypes.c_int
     lib.apde_plan_upload.argtypes = [_vp, _dp, _dp, _dp, _dp]
+    lib.apde_plan_upload_rows.restype = ctypes.c_int
+    lib.apde_plan_upload_rows.argtypes = [_vp, _i64, _i64, _dp, _dp, _dp, _dp]
+    lib.apde_plan_download_rows.restype = ctypes.c_int
+    lib.apde_plan_download_rows.argtypes = [_vp, _i64, _i64, _dp]
     lib.apde_plan_fill.restype = ctypes.c_int
     lib.apde_plan_fill.argtypes = [_vp, ctypes.POINTER(FillDesc)]
     lib.apde_plan_download.restype = ctypes.c_int

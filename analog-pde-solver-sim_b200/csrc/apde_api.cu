@@ -139,6 +139,13 @@ int apde_plan_upload(apde_plan *plan, const double *grid, const double *noise_h,
                      const double *noise_v, const double *source) {
     return plan_upload(plan, grid, noise_h, noise_v, source);
 }
+int apde_plan_upload_rows(apde_plan *plan, int64_t row_lo, int64_t row_hi, const double *grid,
+                          const double *noise_h, const double *noise_v, const double *source) {
+    return plan_upload_rows(plan, row_lo, row_hi, grid, noise_h, noise_v, source);
+}
+int apde_plan_download_rows(apde_plan *plan, int64_t row_lo, int64_t row_hi, double *out) {
+    return plan_download_rows(plan, row_lo, row_hi, out);
+}
 int apde_plan_fill(apde_plan *plan, const apde_fill_desc *fill) { return plan_fill(plan, fill); }
 int apde_plan_download(apde_plan *plan, double *grid) { return plan_download(plan, grid); }
 

@@ -20,7 +20,11 @@ struct apde_plan {
     apde::DevBuf src, gh, gv; // source, 1/noise_h, 1/noise_v  (gh[i][j]: link (i,j)-(i,j+1); gv[i][j]: (i,j)-(i+1,j))
     apde::DevBuf resid;       // per-sweep max_change, plan dtype
     apde::DevBuf scratch;     // checksum outputs etc.
+    apde::DevBuf stage;       // float64 staging for host<->device conversion (grown on demand, reused)
     int cur = 0;
+    bool pass_open = false;   // a phase-1 launch wrote part of u[1-cur]; phase 2 completes it and flips
+    int variant = 1;          // 1 = fused streaming kernel (default), 0 = per-colour in-place kernels
+    int64_t row_block = 256;  // rows per work item of the streaming kernel
     int64_t resid_cap = 0;
     int64_t launches = 0;
     bool filled = false;
@@ -36,6 +40,8 @@ int plan_create(apde_plan **out, const apde_plan_desc *d);
 int plan_upload(apde_plan *p, const double *grid, const double *nh, const double *nv, const double *src);
 int plan_fill(apde_plan *p, const apde_fill_desc *f);
 int plan_download(apde_plan *p, double *grid);
+int plan_upload_rows(apde_plan *p, int64_t win_lo, int64_t win_hi, const double *grid, const double *nh, const double *nv, const double *src);
+int plan_download_rows(apde_plan *p, int64_t win_lo, int64_t win_hi, double *out);
 int plan_run(apde_plan *p, int64_t n_sweeps, int64_t sweep_base, int phase, cudaStream_t st);
 int plan_halo(apde_plan *p, int side, void **send_ptr, void **recv_ptr, int64_t *nbytes);
 int plan_read_residuals(apde_plan *p, int64_t first, int64_t count, double *out, cudaStream_t st);

@@ -14,55 +14,14 @@
 // updated (they are the global Dirichlet ring, or the outermost ghost row).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
 #include "apde_plan.h"
+#include "apde_rb_common.cuh"
 
 namespace apde {
-
-// ------------------------------------------------------------------------------------------
-// arithmetic traits
-// ------------------------------------------------------------------------------------------
-template <typename T> struct Ar;
-template <> struct Ar<double> {
-    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
-    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
-    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
-    static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
-    static __device__ __forceinline__ double abs(double a) { return fabs(a); }
-};
-template <> struct Ar<float> {
-    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
-    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
-    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
-    static __device__ __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
-    static __device__ __forceinline__ float abs(float a) { return fabsf(a); }
-};
-
-template <typename T, bool NOISE, bool SRC>
-__device__ __forceinline__ T rb_relax(T un, T us, T uw, T ue, T gn, T gs, T gw, T ge, T sv) {
-    T acc;
-    if (NOISE) {
-        acc = Ar<T>::mul(gn, un);
-        acc = Ar<T>::fma(gs, us, acc);
-        acc = Ar<T>::fma(gw, uw, acc);
-        acc = Ar<T>::fma(ge, ue, acc);
-    } else {
-        acc = Ar<T>::add(un, us);
-        acc = Ar<T>::add(acc, uw);
-        acc = Ar<T>::add(acc, ue);
-    }
-    if (SRC) acc = Ar<T>::sub(acc, sv);
-    return Ar<T>::mul(acc, (T)0.25);
-}
-
-struct Geo {
-    long long pitch, padl;
-    long long lrows, cols, grows;
-    long long row0;        // global row of local row 0
-    long long own_lo, own_hi;  // owned local rows [own_lo, own_hi)
-};
 
 // ==========================================================================================
 // v0: one launch per colour, in place.  Baseline / cross-check variant (40 B/LUP at fp64).
@@ -128,15 +87,13 @@ __global__ void pack_kernel(const double *__restrict__ in, long long in_rows, lo
 template <typename T>
 __global__ void unpack_kernel(const T *__restrict__ in, Geo g, double *__restrict__ out,
                               long long out_row0, long long out_rows) {
-    const long long nrows = g.own_hi - g.own_lo;
-    const long long n = nrows * g.cols;
+    const long long n = out_rows * g.cols;
     for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n;
          k += (long long)gridDim.x * blockDim.x) {
-        const long long r = k / g.cols, j = k - r * g.cols;
-        const long long li = g.own_lo + r;
-        const long long orow = g.row0 + li - out_row0;
-        if (orow < 0 || orow >= out_rows) continue;
-        out[orow * g.cols + j] = (double)in[li * g.pitch + g.padl + j];
+        const long long orow = k / g.cols, j = k - orow * g.cols;
+        const long long li = out_row0 + orow - g.row0;
+        if (li < g.own_lo || li >= g.own_hi) continue;
+        out[k] = (double)in[li * g.pitch + g.padl + j];
     }
 }
 
@@ -225,19 +182,6 @@ __global__ void resid_to_f64_kernel(const T *in, double *out, long long n) {
 // ------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------
-static Geo make_geo(const apde_plan *p) {
-    Geo g;
-    g.pitch = p->pitch;
-    g.padl = p->padl;
-    g.lrows = p->lrows;
-    g.cols = p->d.cols;
-    g.grows = p->d.grows;
-    g.row0 = p->row0;
-    g.own_lo = p->ghost_top;
-    g.own_hi = p->lrows - p->ghost_bot;
-    return g;
-}
-
 int plan_create(apde_plan **out, const apde_plan_desc *d) {
     if (!out || !d) {
         set_error("plan_create: NULL argument");
@@ -246,7 +190,7 @@ int plan_create(apde_plan **out, const apde_plan_desc *d) {
     *out = nullptr;
     if ((d->dtype_bytes != 4 && d->dtype_bytes != 8) || d->grows < 1 || d->cols < 1 ||
         d->row_begin < 0 || d->row_end > d->grows || d->row_begin >= d->row_end ||
-        d->temporal_depth < 1 || d->temporal_depth > 16) {
+        d->temporal_depth < 1 || d->temporal_depth > 4) {
         set_error("plan_create: bad descriptor (dtype=%d grows=%lld cols=%lld rows=[%lld,%lld) depth=%d)",
                   d->dtype_bytes, (long long)d->grows, (long long)d->cols, (long long)d->row_begin,
                   (long long)d->row_end, d->temporal_depth);
@@ -281,7 +225,9 @@ int plan_create(apde_plan **out, const apde_plan_desc *d) {
     p->lrows = p->ghost_top + owned + p->ghost_bot;
     p->row0 = d->row_begin - p->ghost_top;
     p->padl = 64;  // 512 B (fp64) of zero columns: vector alignment + left tile overhang
-    p->pitch = ((p->padl + d->cols + 320 + 63) / 64) * 64;  // right overhang for the widest warp strip
+    p->pitch = ((p->padl + d->cols + 576 + 63) / 64) * 64;  // right overhang: two of the widest warp strips
+    if (const char *v = getenv("APDE_RB_VARIANT")) p->variant = (v[0] == 'v' ? atoi(v + 1) : atoi(v)) ? 1 : 0;
+    if (const char *v = getenv("APDE_ROW_BLOCK")) p->row_block = std::max(8, atoi(v));
     const size_t bytes = p->plane_elems() * (size_t)p->elem;
     int rc = APDE_OK;
     if ((rc = p->u[0].alloc(bytes)) || (rc = p->u[1].alloc(bytes)) ||
@@ -322,57 +268,71 @@ int plan_ensure_resid(apde_plan *p, int64_t cap) {
     return APDE_OK;
 }
 
+// Host arrays cover global rows [win_lo, win_hi) (noise_v: up to min(win_hi, grows-1)); the strip
+// (owned + ghost rows) must lie inside the window.
 template <typename T>
-static int upload_t(apde_plan *p, const double *grid, const double *nh, const double *nv,
-                    const double *src) {
+static int upload_t(apde_plan *p, int64_t win_lo, int64_t win_hi, const double *grid, const double *nh,
+                    const double *nv, const double *src) {
     const Geo g = make_geo(p);
     const int64_t grows = p->d.grows, cols = p->d.cols;
-    // stage only the rows this strip needs
-    const int64_t r0 = p->row0, r1 = p->row0 + p->lrows;  // global rows [r0, r1)
-    DevBuf stage;
-    APDE_TRY(stage.alloc((size_t)(r1 - r0) * cols * 8));
+    const int64_t r0 = p->row0, r1 = p->row0 + p->lrows;  // global rows [r0, r1) the strip holds
+    if (win_lo > r0 || win_hi < r1) {
+        set_error("plan_upload: host window [%lld,%lld) does not cover the strip rows [%lld,%lld)",
+                  (long long)win_lo, (long long)win_hi, (long long)r0, (long long)r1);
+        return APDE_EINVAL;
+    }
+    if (p->d.has_source && !src) {
+        set_error("plan_upload: plan has_source but source is NULL");
+        return APDE_EINVAL;
+    }
+    if (p->d.has_noise && (!nh || !nv)) {
+        set_error("plan_upload: plan has_noise but noise_h/noise_v is NULL");
+        return APDE_EINVAL;
+    }
+    const size_t nrow = (size_t)(r1 - r0), skip = (size_t)(r0 - win_lo);
+    if (p->stage.bytes < nrow * cols * 8) APDE_TRY(p->stage.alloc(nrow * cols * 8));
+    double *stage = p->stage.as<double>();
     const int tb = 256, tg = p->sm_count * 8;
-    APDE_CUDA(cudaMemcpy(stage.p, grid + (size_t)r0 * cols, (size_t)(r1 - r0) * cols * 8, cudaMemcpyHostToDevice));
-    pack_kernel<T, false><<<tg, tb>>>(stage.as<double>(), r1 - r0, cols, r0, p->u[0].as<T>(), g);
+    APDE_CUDA(cudaMemcpyAsync(stage, grid + skip * cols, nrow * cols * 8, cudaMemcpyHostToDevice, 0));
+    pack_kernel<T, false><<<tg, tb>>>(stage, r1 - r0, cols, r0, p->u[0].as<T>(), g);
     if (p->d.has_source) {
-        if (!src) {
-            set_error("plan_upload: plan has_source but source is NULL");
-            return APDE_EINVAL;
-        }
-        APDE_CUDA(cudaMemcpy(stage.p, src + (size_t)r0 * cols, (size_t)(r1 - r0) * cols * 8, cudaMemcpyHostToDevice));
-        pack_kernel<T, false><<<tg, tb>>>(stage.as<double>(), r1 - r0, cols, r0, p->src.as<T>(), g);
+        APDE_CUDA(cudaMemcpyAsync(stage, src + skip * cols, nrow * cols * 8, cudaMemcpyHostToDevice, 0));
+        pack_kernel<T, false><<<tg, tb>>>(stage, r1 - r0, cols, r0, p->src.as<T>(), g);
     }
     if (p->d.has_noise) {
-        if (!nh || !nv) {
-            set_error("plan_upload: plan has_noise but noise_h/noise_v is NULL");
-            return APDE_EINVAL;
-        }
         if (cols > 1) {
-            APDE_CUDA(cudaMemcpy(stage.p, nh + (size_t)r0 * (cols - 1), (size_t)(r1 - r0) * (cols - 1) * 8, cudaMemcpyHostToDevice));
-            pack_kernel<T, true><<<tg, tb>>>(stage.as<double>(), r1 - r0, cols - 1, r0, p->gh.as<T>(), g);
+            APDE_CUDA(cudaMemcpyAsync(stage, nh + skip * (cols - 1), nrow * (cols - 1) * 8, cudaMemcpyHostToDevice, 0));
+            pack_kernel<T, true><<<tg, tb>>>(stage, r1 - r0, cols - 1, r0, p->gh.as<T>(), g);
         }
         const int64_t v1 = std::min<int64_t>(r1, grows - 1);  // noise_v has grows-1 rows
         if (v1 > r0) {
-            APDE_CUDA(cudaMemcpy(stage.p, nv + (size_t)r0 * cols, (size_t)(v1 - r0) * cols * 8, cudaMemcpyHostToDevice));
-            pack_kernel<T, true><<<tg, tb>>>(stage.as<double>(), v1 - r0, cols, r0, p->gv.as<T>(), g);
+            APDE_CUDA(cudaMemcpyAsync(stage, nv + skip * cols, (size_t)(v1 - r0) * cols * 8, cudaMemcpyHostToDevice, 0));
+            pack_kernel<T, true><<<tg, tb>>>(stage, v1 - r0, cols, r0, p->gv.as<T>(), g);
         }
     }
     APDE_CUDA(cudaGetLastError());
-    APDE_CUDA(cudaMemcpy(p->u[1].p, p->u[0].p, p->plane_elems() * sizeof(T), cudaMemcpyDeviceToDevice));
-    APDE_CUDA(cudaDeviceSynchronize());
+    APDE_CUDA(cudaMemcpyAsync(p->u[1].p, p->u[0].p, p->plane_elems() * sizeof(T), cudaMemcpyDeviceToDevice, 0));
+    APDE_CUDA(cudaStreamSynchronize(0));
     p->cur = 0;
+    p->pass_open = false;
     p->filled = true;
     p->launches += 1 + (p->d.has_source ? 1 : 0) + (p->d.has_noise ? 2 : 0);
     return APDE_OK;
 }
 
-int plan_upload(apde_plan *p, const double *grid, const double *nh, const double *nv, const double *src) {
+int plan_upload_rows(apde_plan *p, int64_t win_lo, int64_t win_hi, const double *grid, const double *nh,
+                     const double *nv, const double *src) {
     if (!p || !grid) {
         set_error("plan_upload: NULL argument");
         return APDE_EINVAL;
     }
     APDE_CUDA(cudaSetDevice(p->device));
-    return p->elem == 8 ? upload_t<double>(p, grid, nh, nv, src) : upload_t<float>(p, grid, nh, nv, src);
+    return p->elem == 8 ? upload_t<double>(p, win_lo, win_hi, grid, nh, nv, src)
+                        : upload_t<float>(p, win_lo, win_hi, grid, nh, nv, src);
+}
+
+int plan_upload(apde_plan *p, const double *grid, const double *nh, const double *nv, const double *src) {
+    return plan_upload_rows(p, 0, p ? p->d.grows : 0, grid, nh, nv, src);
 }
 
 template <typename T> static int fill_t(apde_plan *p, const apde_fill_desc *f) {
@@ -398,25 +358,31 @@ int plan_fill(apde_plan *p, const apde_fill_desc *f) {
     return p->elem == 8 ? fill_t<double>(p, f) : fill_t<float>(p, f);
 }
 
-int plan_download(apde_plan *p, double *grid) {
-    if (!p || !grid) {
-        set_error("plan_download: NULL argument");
+// `out` covers global rows [win_lo, win_hi); the owned rows inside the window are written.
+int plan_download_rows(apde_plan *p, int64_t win_lo, int64_t win_hi, double *out) {
+    if (!p || !out || win_lo < 0 || win_hi > p->d.grows || win_lo >= win_hi) {
+        set_error("plan_download: bad argument");
         return APDE_EINVAL;
     }
     APDE_CUDA(cudaSetDevice(p->device));
     const Geo g = make_geo(p);
-    const int64_t owned = g.own_hi - g.own_lo;
-    DevBuf stage;
-    APDE_TRY(stage.alloc((size_t)owned * g.cols * 8));
-    const int64_t out_row0 = p->d.row_begin;
+    const int64_t lo = std::max<int64_t>(win_lo, p->d.row_begin), hi = std::min<int64_t>(win_hi, p->d.row_end);
+    if (lo >= hi) return APDE_OK;
+    const size_t nrow = (size_t)(hi - lo);
+    if (p->stage.bytes < nrow * g.cols * 8) APDE_TRY(p->stage.alloc(nrow * g.cols * 8));
+    double *stage = p->stage.as<double>();
     if (p->elem == 8)
-        unpack_kernel<double><<<p->sm_count * 8, 256>>>(p->u[p->cur].as<double>(), g, stage.as<double>(), out_row0, owned);
+        unpack_kernel<double><<<p->sm_count * 8, 256>>>(p->u[p->cur].as<double>(), g, stage, lo, hi - lo);
     else
-        unpack_kernel<float><<<p->sm_count * 8, 256>>>(p->u[p->cur].as<float>(), g, stage.as<double>(), out_row0, owned);
+        unpack_kernel<float><<<p->sm_count * 8, 256>>>(p->u[p->cur].as<float>(), g, stage, lo, hi - lo);
     APDE_CUDA(cudaGetLastError());
-    APDE_CUDA(cudaMemcpy(grid + (size_t)out_row0 * g.cols, stage.p, (size_t)owned * g.cols * 8, cudaMemcpyDeviceToHost));
+    APDE_CUDA(cudaMemcpy(out + (size_t)(lo - win_lo) * g.cols, stage, nrow * g.cols * 8, cudaMemcpyDeviceToHost));
     p->launches += 1;
     return APDE_OK;
+}
+
+int plan_download(apde_plan *p, double *grid) {
+    return plan_download_rows(p, 0, p ? p->d.grows : 1, grid);
 }
 
 // ---- v0 driver ---------------------------------------------------------------------------
@@ -442,6 +408,8 @@ static int run_v0(apde_plan *p, int64_t n_sweeps, int64_t sweep_base, cudaStream
 
 template <typename T>
 static int run_dispatch(apde_plan *p, int64_t n, int64_t base, int phase, cudaStream_t st) {
+    if (p->variant == 1)
+        return sizeof(T) == 8 ? run_stream_f64(p, n, base, phase, st) : run_stream_f32(p, n, base, phase, st);
     if (phase == 2) return APDE_OK;  // v0 does everything in phase 0/1
     const bool N = p->d.has_noise, S = p->d.has_source;
     if (N && S) return run_v0<T, true, true>(p, n, base, st);
@@ -481,7 +449,8 @@ int plan_halo(apde_plan *p, int side, void **send_ptr, void **recv_ptr, int64_t 
         set_error("plan_halo: bad argument");
         return APDE_EINVAL;
     }
-    char *base = (char *)p->u[p->cur].p;
+    // after a phase-1 launch the fresh rows live in the buffer the open pass is writing
+    char *base = (char *)p->u[p->pass_open ? 1 - p->cur : p->cur].p;
     const size_t rowb = (size_t)p->pitch * p->elem;
     *nbytes = (int64_t)(p->halo * rowb);
     *send_ptr = *recv_ptr = nullptr;

@@ -118,6 +118,13 @@ int apde_plan_destroy(apde_plan *plan);
 /* Upload host float64 arrays covering the GLOBAL grid (only this strip's rows are read). */
 int apde_plan_upload(apde_plan *plan, const double *grid, const double *noise_h,
                      const double *noise_v, const double *source);
+/* Same with host arrays that hold only global rows [row_lo, row_hi) (noise_v: up to
+ * min(row_hi, grows-1)); the window must cover the strip's owned + ghost rows.  Lets every rank of
+ * a multi-GPU run keep just its own rows in (pinned) host memory. */
+int apde_plan_upload_rows(apde_plan *plan, int64_t row_lo, int64_t row_hi, const double *grid,
+                          const double *noise_h, const double *noise_v, const double *source);
+/* Copy the owned rows that fall inside [row_lo, row_hi) into `out`, which holds exactly that window. */
+int apde_plan_download_rows(apde_plan *plan, int64_t row_lo, int64_t row_hi, double *out);
 /* Generate inputs on the device. */
 int apde_plan_fill(apde_plan *plan, const apde_fill_desc *fill);
 /* Copy this strip's owned rows into a GLOBAL host float64 grid. */

@@ -20,7 +20,8 @@ SHAPES = [(3, 3), (4, 5), (5, 4), (17, 33), (64, 64), (65, 130), (130, 67), (257
 @pytest.mark.parametrize("sigma,src", [(0.0, False), (0.0, True), (0.01, False), (0.02, True)])
 @pytest.mark.parametrize("mode,dt", [("redblack", np.float64), ("redblack32", np.float32)])
 @pytest.mark.parametrize("depth", [1, 2, 3, 4])
-def test_fixed_sweeps_bit_exact_vs_rb_oracle(rows, cols, sigma, src, mode, dt, depth):
+def test_fixed_sweeps_bit_exact_vs_rb_oracle(rows, cols, sigma, src, mode, dt, depth, monkeypatch):
+    monkeypatch.setenv("APDE_ROW_BLOCK", "40")  # several row blocks even on these small grids
     k = 9
     g0, nh, nv, s = random_problem(rows, cols, sigma, seed=rows * 131 + cols, with_source=src)
     ru, rh, _ = oracle.red_black(g0, nh, nv, s, k, dtype=dt)
@@ -29,6 +30,29 @@ def test_fixed_sweeps_bit_exact_vs_rb_oracle(rows, cols, sigma, src, mode, dt, d
     assert n == k
     assert hist.astype(dt).tobytes() == rh.tobytes()
     assert g.astype(dt).tobytes() == ru.tobytes()
+
+
+@pytest.mark.parametrize("rows,cols", [(5, 4), (64, 64), (257, 300)])
+@pytest.mark.parametrize("mode,dt", [("redblack", np.float64), ("redblack32", np.float32)])
+def test_per_colour_variant_equals_oracle(rows, cols, mode, dt, monkeypatch):
+    """APDE_RB_VARIANT=v0 (one in-place launch per colour): the cross-check kernel."""
+    monkeypatch.setenv("APDE_RB_VARIANT", "v0")
+    g0, nh, nv, s = random_problem(rows, cols, 0.01, seed=3)
+    ru, rh, _ = oracle.red_black(g0, nh, nv, s, 7, dtype=dt)
+    g = g0.copy()
+    hist, n, _ = _backend.solve(mode, g, nh, nv, s, 0.0, 7, check_every=7)
+    assert g.astype(dt).tobytes() == ru.tobytes() and hist.astype(dt).tobytes() == rh.tobytes()
+
+
+def test_large_grid_row_blocks_and_strips_of_the_streaming_kernel():
+    """2048 x 1500: many column strips x row blocks per pass, all four depths, vs the oracle."""
+    rows, cols = 2048, 1500
+    g0, nh, nv, s = random_problem(rows, cols, 0.01, seed=21)
+    for depth, k in ((4, 8), (3, 7), (2, 5), (1, 2)):
+        ru, rh, _ = oracle.red_black(g0, nh, nv, s, k, dtype=np.float64)
+        g = g0.copy()
+        hist, n, _ = _backend.solve("redblack", g, nh, nv, s, 0.0, k, check_every=k, temporal_depth=depth)
+        assert g.tobytes() == ru.tobytes() and hist.tobytes() == rh.tobytes()
 
 
 def test_converged_fp64_within_1e10_of_reference_answer():
