@@ -24,6 +24,7 @@ struct apde_plan {
     int cur = 0;
     bool pass_open = false;   // a phase-1 launch wrote part of u[1-cur]; phase 2 completes it and flips
     int variant = 1;          // 1 = fused streaming kernel (default), 0 = per-colour in-place kernels
+    int lane_vectors = 1;     // 16-byte vectors per lane per row in the streaming kernel (1 or 2)
     int64_t row_block = 256;  // rows per work item of the streaming kernel
     int64_t resid_cap = 0;
     int64_t launches = 0;

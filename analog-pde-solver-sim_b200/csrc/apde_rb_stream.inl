@@ -20,6 +20,7 @@
 // are recomputed (garbage creeps in one node per stage from the open edges and never reaches
 // the stored region).  The Dirichlet ring and the padding are never updated.
 #include <algorithm>
+#include <type_traits>
 
 #include "apde_rb_common.cuh"
 
@@ -43,6 +44,25 @@ struct StreamArgs {
     long long blk_b0, blk_bn;      // ... and [blk_b0, blk_b0+blk_bn)
     long long n_strips, n_items;
 };
+
+template <int I, int N, typename F>
+__device__ __forceinline__ void static_for(F &&f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+
+constexpr int RBS_OPF = 3;  // iterations an operand row is prefetched into L1 before its first use
+
+__device__ __forceinline__ void prefetch_l1(const void *p) {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+// |x| on the bit pattern (integer pipe) instead of an fp64-pipe instruction
+__device__ __forceinline__ double abs_bits(double x) {
+    return __hiloint2double(__double2hiint(x) & 0x7fffffff, __double2loint(x));
+}
+__device__ __forceinline__ float abs_bits(float x) { return fabsf(x); }
 
 template <int C>
 __device__ __forceinline__ void load_row(T (&w)[C], const T *p) {
@@ -102,6 +122,7 @@ __global__ void __launch_bounds__(RBS_THREADS) rb_stream_kernel(const StreamArgs
     const int lane = threadIdx.x & 31;
     const long long warp_id = (long long)blockIdx.x * (RBS_THREADS / 32) + (threadIdx.x >> 5);
     const long long n_warps = (long long)gridDim.x * (RBS_THREADS / 32);
+    const long long pitch = a.pitch;
 
     T mx[TD];
 #pragma unroll
@@ -111,8 +132,9 @@ __global__ void __launch_bounds__(RBS_THREADS) rb_stream_kernel(const StreamArgs
         const long long bsel = item / a.n_strips;
         const long long sidx = item - bsel * a.n_strips;
         const long long blk = bsel < a.blk_an ? a.blk_a0 + bsel : a.blk_b0 + (bsel - a.blk_an);
-        const long long rb0 = a.own_lo + blk * a.rbh;
-        const long long rb1 = min(rb0 + a.rbh, a.own_hi);
+        // local row indices fit 32 bits; only element offsets are 64-bit (carried in the pointers)
+        const int rb0 = (int)(a.own_lo + blk * a.rbh);
+        const int rb1 = (int)min((long long)rb0 + a.rbh, a.own_hi);
         const long long jl0 = sidx * VW - HCA + (long long)C * lane;  // first column of this lane (even)
         const bool lane_valid = (C * lane >= HCA) && (C * lane < CW - HCA) && (jl0 < a.cols);
         unsigned colmask = 0;  // bit q: column jl0+q is an interior column
@@ -120,12 +142,20 @@ __global__ void __launch_bounds__(RBS_THREADS) rb_stream_kernel(const StreamArgs
         for (int q = 0; q < C; ++q)
             if (jl0 + q >= 1 && jl0 + q <= a.cols - 2) colmask |= 1u << q;
 
-        const long long ra = max(rb0 - NS, 0ll);             // first streamed row (never updated)
-        const long long re = min(rb1 + NS, a.lrows) - 1;     // last streamed row (never updated)
-        const long long rs = ra - ((a.row0 + ra) & 1);       // even global row: static colour parity
-        const long long r_last = rb1 - 1 + NS;
+        const int ra = max(rb0 - NS, 0);                          // first streamed row (never relaxed)
+        const int re = (int)min((long long)rb1 + NS, a.lrows) - 1;  // last streamed row (never relaxed)
+        const int rs = ra - (int)((a.row0 + ra) & 1);             // even global row: static colour parity
+        const int r_last = rb1 - 1 + NS;
+        // rows in (ra, re) are relaxed (the global ring rows and the outermost ghost rows always sit
+        // at ra / re, never inside); rows in [rb0, rb1) are stored and counted
+        const unsigned upd_span = (unsigned)max(re - ra - 1, 0), own_span = (unsigned)(rb1 - rb0);
 
         const long long lane_off = a.padl + jl0;
+        const T *pin = a.in + (long long)rs * pitch + lane_off;            // row r
+        T *pout = a.out + (long long)(rs - NS) * pitch + lane_off;         // row r - NS
+        const long long st0 = (long long)(rs - 1) * pitch + lane_off;      // row r - 1 (stage 0's row)
+        const T *psrc = a.src + st0, *pgh = a.gh + st0, *pgv = a.gv + st0;
+
         T w[NW][C];
 #pragma unroll
         for (int k = 0; k < NW; ++k)
@@ -133,63 +163,97 @@ __global__ void __launch_bounds__(RBS_THREADS) rb_stream_kernel(const StreamArgs
             for (int q = 0; q < C; ++q) w[k][q] = (T)0;
 #pragma unroll
         for (int k = 0; k < RBS_PF; ++k) {
-            const long long r = rs + k;
-            if (r >= 0 && r <= re) load_row<C>(w[k], a.in + r * a.pitch + lane_off);
+            const int r = rs + k;
+            if (r >= 0 && r <= re) load_row<C>(w[k], pin + k * pitch);
         }
+        unsigned act = 0, cnt = 0;  // bit s: the row stage s handles this iteration is relaxed / counted
+        T mxl[TD];
+#pragma unroll
+        for (int t = 0; t < TD; ++t) mxl[t] = (T)0;
 
-        for (long long base = 0; rs + base <= r_last; base += NW) {
+        for (int rc = rs; rc <= r_last; rc += NW) {
 #pragma unroll
             for (int rr = 0; rr < NW; ++rr) {
-                const long long r = rs + base + rr;
-                if (r <= r_last) {
-                    {   // prefetch row r+PF into its future slot
-                        const long long rp = r + RBS_PF;
-                        if (rp <= re) load_row<C>(w[(rr + RBS_PF) % NW], a.in + rp * a.pitch + lane_off);
+                const int r = rc + rr;
+                if (r + RBS_PF <= re) load_row<C>(w[(rr + RBS_PF) % NW], pin + RBS_PF * pitch);
+                act = (act << 1) | (((unsigned)(r - 2 - ra) < upd_span) ? 1u : 0u);
+                cnt = (cnt << 1) | (((unsigned)(r - 1 - rb0) < own_span) ? 1u : 0u);
+                const int p = (rr + 1) & 1;  // column parity relaxed in this iteration (all stages)
+                // Operand rows (source / conductances) are pulled into L1 RBS_OPF iterations before
+                // their first use, then every stage's operands are loaded at the top of the
+                // iteration (L1 hits) so the loads overlap the dependent stage chain.
+                if (r + RBS_OPF - 1 <= re) {
+                    if (SRC) prefetch_l1(psrc + (long long)RBS_OPF * pitch);
+                    if (NOISE) {
+                        prefetch_l1(pgh + (long long)RBS_OPF * pitch);
+                        prefetch_l1(pgv + (long long)RBS_OPF * pitch);
                     }
-                    const int p = (rr + 1) & 1;  // column parity relaxed in this iteration (all stages)
+                }
+                constexpr int CH = (C + 1) / 2;
+                // operands of the first LA stages are fetched up front, the rest one stage ahead
+                // (all of them when only the source is read; conductances would cost too many registers)
+                constexpr int LA = NOISE ? 1 : NS;
+                T o_sv[NS][CH], o_gn[NOISE ? NS : 1][CH], o_gs[NOISE ? NS : 1][CH], o_gw[NOISE ? NS : 1][CH], o_ge[NOISE ? NS : 1][CH];
+                auto fetch = [&](auto s_tag) {
+                    constexpr int s = decltype(s_tag)::value;
+                    const bool act_s = (act >> s) & 1u;
+                    const long long ro = -(long long)s * pitch;
 #pragma unroll
-                    for (int s = 0; s < NS; ++s) {
-                        const long long i = r - 1 - s;
-                        if (i > ra && i < re) {
-                            const int si = (rr - 1 - s + 4 * NW) % NW;
-                            const int su = (si + NW - 1) % NW, sd = (si + 1) % NW;
-                            const long long gi = a.row0 + i;
-                            const bool row_upd = gi > 0 && gi < a.grows - 1;
-                            const bool row_cnt = lane_valid && i >= rb0 && i < rb1;
-                            const long long e0 = i * a.pitch + lane_off;
-                            // the one cross-lane operand of this stage-row
-                            T edge;
-                            if (p == 0) {
-                                edge = __shfl_up_sync(0xffffffffu, w[si][C - 1], 1);
-                            } else {
-                                edge = __shfl_down_sync(0xffffffffu, w[si][0], 1);
-                            }
-#pragma unroll
-                            for (int q = p; q < C; q += 2) {
-                                const T lf = (q > 0) ? w[si][q - 1] : edge;
-                                const T rt = (q < C - 1) ? w[si][q + 1] : edge;
-                                T gn = (T)1, gs = (T)1, gw = (T)1, ge = (T)1, sv = (T)0;
-                                if (NOISE) {
-                                    gn = __ldg(a.gv + e0 - a.pitch + q);
-                                    gs = __ldg(a.gv + e0 + q);
-                                    gw = __ldg(a.gh + e0 + q - 1);
-                                    ge = __ldg(a.gh + e0 + q);
-                                }
-                                if (SRC) sv = __ldg(a.src + e0 + q);
-                                const T old = w[si][q];
-                                const T nw = rb_relax<T, NOISE, SRC>(w[su][q], w[sd][q], lf, rt, gn, gs, gw, ge, sv);
-                                if (row_upd && ((colmask >> q) & 1u)) {
-                                    w[si][q] = nw;
-                                    if (row_cnt) mx[s >> 1] = max_ignore_nan(mx[s >> 1], Ar<T>::abs(Ar<T>::sub(nw, old)));
-                                }
-                            }
+                    for (int q = p; q < C; q += 2) {
+                        if (SRC) o_sv[s][q >> 1] = act_s ? __ldg(psrc + ro + q) : (T)0;
+                        if (NOISE) {
+                            o_gn[s][q >> 1] = act_s ? __ldg(pgv + ro - pitch + q) : (T)0;
+                            o_gs[s][q >> 1] = act_s ? __ldg(pgv + ro + q) : (T)0;
+                            o_gw[s][q >> 1] = act_s ? __ldg(pgh + ro + q - 1) : (T)0;
+                            o_ge[s][q >> 1] = act_s ? __ldg(pgh + ro + q) : (T)0;
                         }
                     }
-                    const long long o = r - NS;  // this row has passed all stages
-                    if (lane_valid && o >= rb0 && o < rb1)
-                        store_row<C>(a.out + o * a.pitch + lane_off, w[(rr - NS + 4 * NW) % NW]);
-                }
+                };
+                static_for<0, LA>(fetch);
+                static_for<0, NS>([&](auto s_tag) {
+                    constexpr int s = decltype(s_tag)::value;
+                    if constexpr (s + LA < NS) fetch(std::integral_constant<int, s + LA>{});
+                    // stage s relaxes colour s&1 of row r-1-s; everything is predicated, no branches
+                    const int si = (rr - 1 - s + 4 * NW) % NW;
+                    const int su = (si + NW - 1) % NW, sd = (si + 1) % NW;
+                    const bool act_s = (act >> s) & 1u;
+                    const bool cnt_s = (cnt >> s) & 1u;
+                    const unsigned okmask = act_s ? colmask : 0u;
+                    T edge;  // the one cross-lane operand of this stage-row
+                    if (p == 0) edge = __shfl_up_sync(0xffffffffu, w[si][C - 1], 1);
+                    else edge = __shfl_down_sync(0xffffffffu, w[si][0], 1);
+#pragma unroll
+                    for (int q = p; q < C; q += 2) {
+                        const T lf = (q > 0) ? w[si][q - 1] : edge;
+                        const T rt = (q < C - 1) ? w[si][q + 1] : edge;
+                        T gn = (T)1, gs = (T)1, gw = (T)1, ge = (T)1, sv = (T)0;
+                        if (NOISE) {
+                            gn = o_gn[s][q >> 1];
+                            gs = o_gs[s][q >> 1];
+                            gw = o_gw[s][q >> 1];
+                            ge = o_ge[s][q >> 1];
+                        }
+                        if (SRC) sv = o_sv[s][q >> 1];
+                        const T old = w[si][q];
+                        const T nw = rb_relax<T, NOISE, SRC>(w[su][q], w[sd][q], lf, rt, gn, gs, gw, ge, sv);
+                        const T keep = ((okmask >> q) & 1u) ? nw : old;
+                        w[si][q] = keep;
+                        const T ch = abs_bits(Ar<T>::sub(keep, old));
+                        if (cnt_s && ch > mxl[s >> 1]) mxl[s >> 1] = ch;
+                    }
+                });
+                // row r-NS has passed every stage
+                if (lane_valid && (unsigned)(r - NS - rb0) < own_span) store_row<C>(pout, w[(rr - NS + 4 * NW) % NW]);
+                pin += pitch;
+                pout += pitch;
+                psrc += pitch;
+                pgh += pitch;
+                pgv += pitch;
             }
+        }
+        if (lane_valid) {
+#pragma unroll
+            for (int t = 0; t < TD; ++t) mx[t] = max_ignore_nan(mx[t], mxl[t]);
         }
     }
 #pragma unroll
@@ -229,7 +293,17 @@ int launch_depth(apde_plan *p, const StreamArgs &a, int td, cudaStream_t st) {
     return APDE_EINVAL;
 }
 
-constexpr int RBS_C = 16 / (int)sizeof(T);  // one 16-byte vector per lane
+constexpr int RBS_C1 = 16 / (int)sizeof(T);  // one 16-byte vector per lane
+constexpr int RBS_C2 = 32 / (int)sizeof(T);  // two
+
+template <int C>
+int launch_any(apde_plan *p, const StreamArgs &a, int td, cudaStream_t st) {
+    const bool N = p->d.has_noise, S = p->d.has_source;
+    if (N && S) return launch_depth<C, true, true>(p, a, td, st);
+    if (N) return launch_depth<C, true, false>(p, a, td, st);
+    if (S) return launch_depth<C, false, true>(p, a, td, st);
+    return launch_depth<C, false, false>(p, a, td, st);
+}
 
 }  // namespace
 
@@ -267,8 +341,9 @@ int RBS_FN(apde_plan *p, int64_t n_sweeps, int64_t sweep_base, int phase, cudaSt
         const long long owned = g.own_hi - g.own_lo;
         a.rbh = p->row_block;
         const long long nblk = (owned + a.rbh - 1) / a.rbh;
-        const int HCA = ((2 * td + RBS_C - 1) / RBS_C) * RBS_C;
-        const int VW = 32 * RBS_C - 2 * HCA;
+        const int lane_cols = p->lane_vectors == 2 ? RBS_C2 : RBS_C1;
+        const int HCA = ((2 * td + lane_cols - 1) / lane_cols) * lane_cols;
+        const int VW = 32 * lane_cols - 2 * HCA;
         a.n_strips = (g.cols + VW - 1) / VW;
         // edge blocks: first / last row block when that side has a neighbour strip
         const bool top_nb = p->ghost_top > 0, bot_nb = p->ghost_bot > 0;
@@ -283,12 +358,7 @@ int RBS_FN(apde_plan *p, int64_t n_sweeps, int64_t sweep_base, int phase, cudaSt
         }
         a.n_items = (a.blk_an + a.blk_bn) * a.n_strips;
         if (a.n_items > 0) {
-            const bool N = p->d.has_noise, S = p->d.has_source;
-            int rc;
-            if (N && S) rc = launch_depth<RBS_C, true, true>(p, a, td, st);
-            else if (N) rc = launch_depth<RBS_C, true, false>(p, a, td, st);
-            else if (S) rc = launch_depth<RBS_C, false, true>(p, a, td, st);
-            else rc = launch_depth<RBS_C, false, false>(p, a, td, st);
+            const int rc = p->lane_vectors == 2 ? launch_any<RBS_C2>(p, a, td, st) : launch_any<RBS_C1>(p, a, td, st);
             if (rc != APDE_OK) return rc;
         }
         if (phase == 1) {

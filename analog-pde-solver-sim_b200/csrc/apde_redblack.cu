@@ -227,6 +227,7 @@ int plan_create(apde_plan **out, const apde_plan_desc *d) {
     p->padl = 64;  // 512 B (fp64) of zero columns: vector alignment + left tile overhang
     p->pitch = ((p->padl + d->cols + 576 + 63) / 64) * 64;  // right overhang: two of the widest warp strips
     if (const char *v = getenv("APDE_RB_VARIANT")) p->variant = (v[0] == 'v' ? atoi(v + 1) : atoi(v)) ? 1 : 0;
+    if (const char *v = getenv("APDE_LANE_VECTORS")) p->lane_vectors = atoi(v) == 2 ? 2 : 1;
     if (const char *v = getenv("APDE_ROW_BLOCK")) p->row_block = std::max(8, atoi(v));
     const size_t bytes = p->plane_elems() * (size_t)p->elem;
     int rc = APDE_OK;
