@@ -30,7 +30,14 @@ struct apde_plan {
     int64_t launches = 0;
     bool filled = false;
 
-    size_t plane_elems() const { return (size_t)lrows * (size_t)pitch; }
+    int64_t rowpad = 32;      // zero rows above and below every array: the streaming kernel may read
+                              // (never write) a few rows past either end without clamping
+    size_t plane_elems() const { return (size_t)(lrows + 2 * rowpad) * (size_t)pitch; }
+    // pointers to local row 0 (past the top padding)
+    template <typename T> T *U(int k) const { return u[k].as<T>() + rowpad * pitch; }
+    template <typename T> T *S() const { return src.p ? src.as<T>() + rowpad * pitch : nullptr; }
+    template <typename T> T *GH() const { return gh.p ? gh.as<T>() + rowpad * pitch : nullptr; }
+    template <typename T> T *GV() const { return gv.p ? gv.as<T>() + rowpad * pitch : nullptr; }
     // element offset of (local row li, column j)
     size_t off(int64_t li, int64_t j) const { return (size_t)li * (size_t)pitch + (size_t)(padl + j); }
 };

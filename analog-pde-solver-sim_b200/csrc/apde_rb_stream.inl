@@ -31,6 +31,13 @@ using T = RBS_T;
 
 constexpr int RBS_THREADS = 128;
 constexpr int RBS_PF = 2;  // rows prefetched ahead (kept even so the unroll period stays even)
+#ifndef RBS_LAG
+#define RBS_LAG 1
+#endif
+// Rows between consecutive half-sweep stages.  1: stage s+1 consumes what stage s produced in the
+// same iteration (one long dependent chain, smallest register window).  2: every stage of an
+// iteration is independent of the others (NS-way instruction-level parallelism, NS more window rows).
+constexpr int LAG = RBS_LAG;
 
 struct StreamArgs {
     const T *in;
@@ -113,7 +120,8 @@ __device__ __forceinline__ void store_row(T *p, const T (&w)[C]) {
 template <int C, int TD, bool NOISE, bool SRC>
 __global__ void __launch_bounds__(RBS_THREADS) rb_stream_kernel(const StreamArgs a) {
     constexpr int NS = 2 * TD;             // half-sweep stages
-    constexpr int NW = NS + 2 + RBS_PF;    // register window rows (even)
+    constexpr int DEPTH_ROWS = 1 + LAG * (NS - 1);            // newest-to-final distance in rows
+    constexpr int NW = ((DEPTH_ROWS + 2 + 1) / 2) * 2 + RBS_PF;  // register window rows (even)
     constexpr int CW = 32 * C;             // columns per warp strip
     constexpr int HCA = ((NS + C - 1) / C) * C;  // column halo, lane aligned
     constexpr int VW = CW - 2 * HCA;       // columns a strip stores
@@ -145,14 +153,14 @@ __global__ void __launch_bounds__(RBS_THREADS) rb_stream_kernel(const StreamArgs
         const int ra = max(rb0 - NS, 0);                          // first streamed row (never relaxed)
         const int re = (int)min((long long)rb1 + NS, a.lrows) - 1;  // last streamed row (never relaxed)
         const int rs = ra - (int)((a.row0 + ra) & 1);             // even global row: static colour parity
-        const int r_last = rb1 - 1 + NS;
+        const int r_last = rb1 - 1 + DEPTH_ROWS;
         // rows in (ra, re) are relaxed (the global ring rows and the outermost ghost rows always sit
         // at ra / re, never inside); rows in [rb0, rb1) are stored and counted
         const unsigned upd_span = (unsigned)max(re - ra - 1, 0), own_span = (unsigned)(rb1 - rb0);
 
         const long long lane_off = a.padl + jl0;
         const T *pin = a.in + (long long)rs * pitch + lane_off;            // row r
-        T *pout = a.out + (long long)(rs - NS) * pitch + lane_off;         // row r - NS
+        T *pout = a.out + (long long)(rs - DEPTH_ROWS) * pitch + lane_off; // row r - DEPTH_ROWS
         const long long st0 = (long long)(rs - 1) * pitch + lane_off;      // row r - 1 (stage 0's row)
         const T *psrc = a.src + st0, *pgh = a.gh + st0, *pgv = a.gv + st0;
 
@@ -164,7 +172,7 @@ __global__ void __launch_bounds__(RBS_THREADS) rb_stream_kernel(const StreamArgs
 #pragma unroll
         for (int k = 0; k < RBS_PF; ++k) {
             const int r = rs + k;
-            if (r >= 0 && r <= re) load_row<C>(w[k], pin + k * pitch);
+            load_row<C>(w[k], pin + k * pitch);  // rows past either end are zero padding
         }
         unsigned act = 0, cnt = 0;  // bit s: the row stage s handles this iteration is relaxed / counted
         T mxl[TD];
@@ -175,19 +183,19 @@ __global__ void __launch_bounds__(RBS_THREADS) rb_stream_kernel(const StreamArgs
 #pragma unroll
             for (int rr = 0; rr < NW; ++rr) {
                 const int r = rc + rr;
-                if (r + RBS_PF <= re) load_row<C>(w[(rr + RBS_PF) % NW], pin + RBS_PF * pitch);
+                // unconditional (padding rows make every address valid): the load lands straight in
+                // its window slot and nothing waits on it until the row is first used
+                load_row<C>(w[(rr + RBS_PF) % NW], pin + RBS_PF * pitch);
                 act = (act << 1) | (((unsigned)(r - 2 - ra) < upd_span) ? 1u : 0u);
                 cnt = (cnt << 1) | (((unsigned)(r - 1 - rb0) < own_span) ? 1u : 0u);
-                const int p = (rr + 1) & 1;  // column parity relaxed in this iteration (all stages)
+                // column parity relaxed by stage s in this iteration: (rr + 1 + (LAG-1)*s) & 1
                 // Operand rows (source / conductances) are pulled into L1 RBS_OPF iterations before
                 // their first use, then every stage's operands are loaded at the top of the
                 // iteration (L1 hits) so the loads overlap the dependent stage chain.
-                if (r + RBS_OPF - 1 <= re) {
-                    if (SRC) prefetch_l1(psrc + (long long)RBS_OPF * pitch);
-                    if (NOISE) {
-                        prefetch_l1(pgh + (long long)RBS_OPF * pitch);
-                        prefetch_l1(pgv + (long long)RBS_OPF * pitch);
-                    }
+                if (SRC) prefetch_l1(psrc + (long long)RBS_OPF * pitch);
+                if (NOISE) {
+                    prefetch_l1(pgh + (long long)RBS_OPF * pitch);
+                    prefetch_l1(pgv + (long long)RBS_OPF * pitch);
                 }
                 constexpr int CH = (C + 1) / 2;
                 // operands of the first LA stages are fetched up front, the rest one stage ahead
@@ -196,16 +204,17 @@ __global__ void __launch_bounds__(RBS_THREADS) rb_stream_kernel(const StreamArgs
                 T o_sv[NS][CH], o_gn[NOISE ? NS : 1][CH], o_gs[NOISE ? NS : 1][CH], o_gw[NOISE ? NS : 1][CH], o_ge[NOISE ? NS : 1][CH];
                 auto fetch = [&](auto s_tag) {
                     constexpr int s = decltype(s_tag)::value;
-                    const bool act_s = (act >> s) & 1u;
-                    const long long ro = -(long long)s * pitch;
+                    const long long ro = -(long long)(LAG * s) * pitch;
+                    const int p = (rr + 1 + (LAG - 1) * s) & 1;
 #pragma unroll
                     for (int q = p; q < C; q += 2) {
-                        if (SRC) o_sv[s][q >> 1] = act_s ? __ldg(psrc + ro + q) : (T)0;
+                        // unconditional: rows of inactive stages are padding or real rows, both readable
+                        if (SRC) o_sv[s][q >> 1] = __ldg(psrc + ro + q);
                         if (NOISE) {
-                            o_gn[s][q >> 1] = act_s ? __ldg(pgv + ro - pitch + q) : (T)0;
-                            o_gs[s][q >> 1] = act_s ? __ldg(pgv + ro + q) : (T)0;
-                            o_gw[s][q >> 1] = act_s ? __ldg(pgh + ro + q - 1) : (T)0;
-                            o_ge[s][q >> 1] = act_s ? __ldg(pgh + ro + q) : (T)0;
+                            o_gn[s][q >> 1] = __ldg(pgv + ro - pitch + q);
+                            o_gs[s][q >> 1] = __ldg(pgv + ro + q);
+                            o_gw[s][q >> 1] = __ldg(pgh + ro + q - 1);
+                            o_ge[s][q >> 1] = __ldg(pgh + ro + q);
                         }
                     }
                 };
@@ -213,11 +222,12 @@ __global__ void __launch_bounds__(RBS_THREADS) rb_stream_kernel(const StreamArgs
                 static_for<0, NS>([&](auto s_tag) {
                     constexpr int s = decltype(s_tag)::value;
                     if constexpr (s + LA < NS) fetch(std::integral_constant<int, s + LA>{});
-                    // stage s relaxes colour s&1 of row r-1-s; everything is predicated, no branches
-                    const int si = (rr - 1 - s + 4 * NW) % NW;
+                    // stage s relaxes colour s&1 of row r-1-LAG*s; everything is predicated, no branches
+                    const int p = (rr + 1 + (LAG - 1) * s) & 1;
+                    const int si = (rr - 1 - LAG * s + 8 * NW) % NW;
                     const int su = (si + NW - 1) % NW, sd = (si + 1) % NW;
-                    const bool act_s = (act >> s) & 1u;
-                    const bool cnt_s = (cnt >> s) & 1u;
+                    const bool act_s = (act >> (LAG * s)) & 1u;
+                    const bool cnt_s = (cnt >> (LAG * s)) & 1u;
                     const unsigned okmask = act_s ? colmask : 0u;
                     T edge;  // the one cross-lane operand of this stage-row
                     if (p == 0) edge = __shfl_up_sync(0xffffffffu, w[si][C - 1], 1);
@@ -242,8 +252,9 @@ __global__ void __launch_bounds__(RBS_THREADS) rb_stream_kernel(const StreamArgs
                         if (cnt_s && ch > mxl[s >> 1]) mxl[s >> 1] = ch;
                     }
                 });
-                // row r-NS has passed every stage
-                if (lane_valid && (unsigned)(r - NS - rb0) < own_span) store_row<C>(pout, w[(rr - NS + 4 * NW) % NW]);
+                // row r-DEPTH_ROWS has passed every stage
+                if (lane_valid && (unsigned)(r - DEPTH_ROWS - rb0) < own_span)
+                    store_row<C>(pout, w[(rr - DEPTH_ROWS + 8 * NW) % NW]);
                 pin += pitch;
                 pout += pitch;
                 psrc += pitch;
@@ -324,11 +335,11 @@ int RBS_FN(apde_plan *p, int64_t n_sweeps, int64_t sweep_base, int phase, cudaSt
         // a phase-2 call completes the pass a phase-1 call started: same buffers
         const int src_buf = p->cur, dst_buf = 1 - p->cur;
         StreamArgs a;
-        a.in = p->u[src_buf].as<T>();
-        a.out = p->u[dst_buf].as<T>();
-        a.src = p->src.as<T>();
-        a.gh = p->gh.as<T>();
-        a.gv = p->gv.as<T>();
+        a.in = p->U<T>(src_buf);
+        a.out = p->U<T>(dst_buf);
+        a.src = p->S<T>();
+        a.gh = p->GH<T>();
+        a.gv = p->GV<T>();
         a.resid = p->resid.as<T>() + sweep_base + done;
         a.pitch = g.pitch;
         a.padl = g.padl;

@@ -295,20 +295,20 @@ static int upload_t(apde_plan *p, int64_t win_lo, int64_t win_hi, const double *
     double *stage = p->stage.as<double>();
     const int tb = 256, tg = p->sm_count * 8;
     APDE_CUDA(cudaMemcpyAsync(stage, grid + skip * cols, nrow * cols * 8, cudaMemcpyHostToDevice, 0));
-    pack_kernel<T, false><<<tg, tb>>>(stage, r1 - r0, cols, r0, p->u[0].as<T>(), g);
+    pack_kernel<T, false><<<tg, tb>>>(stage, r1 - r0, cols, r0, p->U<T>(0), g);
     if (p->d.has_source) {
         APDE_CUDA(cudaMemcpyAsync(stage, src + skip * cols, nrow * cols * 8, cudaMemcpyHostToDevice, 0));
-        pack_kernel<T, false><<<tg, tb>>>(stage, r1 - r0, cols, r0, p->src.as<T>(), g);
+        pack_kernel<T, false><<<tg, tb>>>(stage, r1 - r0, cols, r0, p->S<T>(), g);
     }
     if (p->d.has_noise) {
         if (cols > 1) {
             APDE_CUDA(cudaMemcpyAsync(stage, nh + skip * (cols - 1), nrow * (cols - 1) * 8, cudaMemcpyHostToDevice, 0));
-            pack_kernel<T, true><<<tg, tb>>>(stage, r1 - r0, cols - 1, r0, p->gh.as<T>(), g);
+            pack_kernel<T, true><<<tg, tb>>>(stage, r1 - r0, cols - 1, r0, p->GH<T>(), g);
         }
         const int64_t v1 = std::min<int64_t>(r1, grows - 1);  // noise_v has grows-1 rows
         if (v1 > r0) {
             APDE_CUDA(cudaMemcpyAsync(stage, nv + skip * cols, (size_t)(v1 - r0) * cols * 8, cudaMemcpyHostToDevice, 0));
-            pack_kernel<T, true><<<tg, tb>>>(stage, v1 - r0, cols, r0, p->gv.as<T>(), g);
+            pack_kernel<T, true><<<tg, tb>>>(stage, v1 - r0, cols, r0, p->GV<T>(), g);
         }
     }
     APDE_CUDA(cudaGetLastError());
@@ -338,9 +338,9 @@ int plan_upload(apde_plan *p, const double *grid, const double *nh, const double
 
 template <typename T> static int fill_t(apde_plan *p, const apde_fill_desc *f) {
     const Geo g = make_geo(p);
-    fill_kernel<T><<<p->sm_count * 8, 256>>>(p->u[0].as<T>(), p->d.has_source ? p->src.as<T>() : nullptr,
-                                             p->d.has_noise ? p->gh.as<T>() : nullptr,
-                                             p->d.has_noise ? p->gv.as<T>() : nullptr, g, *f);
+    fill_kernel<T><<<p->sm_count * 8, 256>>>(p->U<T>(0), p->S<T>(),
+                                             p->GH<T>(),
+                                             p->GV<T>(), g, *f);
     APDE_CUDA(cudaGetLastError());
     APDE_CUDA(cudaMemcpy(p->u[1].p, p->u[0].p, p->plane_elems() * sizeof(T), cudaMemcpyDeviceToDevice));
     APDE_CUDA(cudaDeviceSynchronize());
@@ -373,9 +373,9 @@ int plan_download_rows(apde_plan *p, int64_t win_lo, int64_t win_hi, double *out
     if (p->stage.bytes < nrow * g.cols * 8) APDE_TRY(p->stage.alloc(nrow * g.cols * 8));
     double *stage = p->stage.as<double>();
     if (p->elem == 8)
-        unpack_kernel<double><<<p->sm_count * 8, 256>>>(p->u[p->cur].as<double>(), g, stage, lo, hi - lo);
+        unpack_kernel<double><<<p->sm_count * 8, 256>>>(p->U<double>(p->cur), g, stage, lo, hi - lo);
     else
-        unpack_kernel<float><<<p->sm_count * 8, 256>>>(p->u[p->cur].as<float>(), g, stage, lo, hi - lo);
+        unpack_kernel<float><<<p->sm_count * 8, 256>>>(p->U<float>(p->cur), g, stage, lo, hi - lo);
     APDE_CUDA(cudaGetLastError());
     APDE_CUDA(cudaMemcpy(out + (size_t)(lo - win_lo) * g.cols, stage, nrow * g.cols * 8, cudaMemcpyDeviceToHost));
     p->launches += 1;
@@ -394,12 +394,12 @@ static int run_v0(apde_plan *p, int64_t n_sweeps, int64_t sweep_base, cudaStream
     if (hw < 1 || g.lrows < 3) return APDE_OK;
     dim3 block(256);
     dim3 grid((unsigned)((hw + 255) / 256), (unsigned)std::min<long long>(g.lrows - 2, 32768));
-    T *u = p->u[p->cur].as<T>();
+    T *u = p->U<T>(p->cur);
     for (int64_t s = 0; s < n_sweeps; ++s) {
         T *slot = p->resid.as<T>() + sweep_base + s;
         for (int colour = 0; colour < 2; ++colour) {
-            rb_colour_kernel<T, NOISE, SRC><<<grid, block, 0, st>>>(u, p->src.as<T>(), p->gh.as<T>(),
-                                                                  p->gv.as<T>(), g, colour, slot);
+            rb_colour_kernel<T, NOISE, SRC><<<grid, block, 0, st>>>(u, p->S<T>(), p->GH<T>(),
+                                                                  p->GV<T>(), g, colour, slot);
             p->launches++;
         }
     }
@@ -451,8 +451,8 @@ int plan_halo(apde_plan *p, int side, void **send_ptr, void **recv_ptr, int64_t 
         return APDE_EINVAL;
     }
     // after a phase-1 launch the fresh rows live in the buffer the open pass is writing
-    char *base = (char *)p->u[p->pass_open ? 1 - p->cur : p->cur].p;
     const size_t rowb = (size_t)p->pitch * p->elem;
+    char *base = (char *)p->u[p->pass_open ? 1 - p->cur : p->cur].p + (size_t)p->rowpad * rowb;
     *nbytes = (int64_t)(p->halo * rowb);
     *send_ptr = *recv_ptr = nullptr;
     if (side == 0 && p->ghost_top) {
@@ -494,9 +494,9 @@ int plan_checksum(apde_plan *p, double *sum_out, double *absmax_out, cudaStream_
     const Geo g = make_geo(p);
     APDE_CUDA(cudaMemsetAsync(p->scratch.p, 0, 16, st));
     if (p->elem == 8)
-        checksum_kernel<double><<<p->sm_count * 4, 256, 0, st>>>(p->u[p->cur].as<double>(), g, p->scratch.as<double>());
+        checksum_kernel<double><<<p->sm_count * 4, 256, 0, st>>>(p->U<double>(p->cur), g, p->scratch.as<double>());
     else
-        checksum_kernel<float><<<p->sm_count * 4, 256, 0, st>>>(p->u[p->cur].as<float>(), g, p->scratch.as<double>());
+        checksum_kernel<float><<<p->sm_count * 4, 256, 0, st>>>(p->U<float>(p->cur), g, p->scratch.as<double>());
     APDE_CUDA(cudaGetLastError());
     p->launches++;
     double h[2];
