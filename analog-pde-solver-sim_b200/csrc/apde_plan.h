@@ -30,7 +30,7 @@ struct apde_plan {
     int64_t launches = 0;
     bool filled = false;
 
-    int64_t rowpad = 32;      // zero rows above and below every array: the streaming kernel may read
+    int64_t rowpad = 48;      // zero rows above and below every array: the streaming kernel may read
                               // (never write) a few rows past either end without clamping
     size_t plane_elems() const { return (size_t)(lrows + 2 * rowpad) * (size_t)pitch; }
     // pointers to local row 0 (past the top padding)

@@ -61,7 +61,20 @@ __device__ __forceinline__ void static_for(F &&f) {
 }
 
 constexpr int RBS_OPF = 3;  // iterations an operand row is prefetched into L1 before its first use
+#ifndef RBS_L2PF
+#define RBS_L2PF 12
+#endif
+constexpr int L2PF = RBS_L2PF;  // rows ahead that are pulled from HBM into L2 (0 = off)
+// Resident blocks per SM the compiler must allow (caps registers).  Measured on B200 (tools/rb_sweep.py):
+// the fp32 source-only kernels gain from 12 warps/SM (168 registers, no spills); every other variant
+// loses more to spills than it gains from occupancy.
+constexpr int rbs_min_blocks(int elem_bytes, int lane_cols, bool noise) {
+    return (elem_bytes == 4 && lane_cols == 4 && !noise) ? 3 : 1;
+}
 
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 __device__ __forceinline__ void prefetch_l1(const void *p) {
     asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
@@ -118,7 +131,7 @@ __device__ __forceinline__ void store_row(T *p, const T (&w)[C]) {
 }
 
 template <int C, int TD, bool NOISE, bool SRC>
-__global__ void __launch_bounds__(RBS_THREADS) rb_stream_kernel(const StreamArgs a) {
+__global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C, NOISE)) rb_stream_kernel(const StreamArgs a) {
     constexpr int NS = 2 * TD;             // half-sweep stages
     constexpr int DEPTH_ROWS = 1 + LAG * (NS - 1);            // newest-to-final distance in rows
     constexpr int NW = ((DEPTH_ROWS + 2 + 1) / 2) * 2 + RBS_PF;  // register window rows (even)
@@ -192,6 +205,16 @@ __global__ void __launch_bounds__(RBS_THREADS) rb_stream_kernel(const StreamArgs
                 // Operand rows (source / conductances) are pulled into L1 RBS_OPF iterations before
                 // their first use, then every stage's operands are loaded at the top of the
                 // iteration (L1 hits) so the loads overlap the dependent stage chain.
+                if (L2PF > 0) {
+                    // two-level software prefetch: HBM -> L2 far ahead (hides DRAM latency at low
+                    // occupancy), L2 -> L1 / registers a few rows ahead
+                    prefetch_l2(pin + (long long)L2PF * pitch);
+                    if (SRC) prefetch_l2(psrc + (long long)L2PF * pitch);
+                    if (NOISE) {
+                        prefetch_l2(pgh + (long long)L2PF * pitch);
+                        prefetch_l2(pgv + (long long)L2PF * pitch);
+                    }
+                }
                 if (SRC) prefetch_l1(psrc + (long long)RBS_OPF * pitch);
                 if (NOISE) {
                     prefetch_l1(pgh + (long long)RBS_OPF * pitch);

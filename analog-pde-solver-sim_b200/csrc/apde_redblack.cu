@@ -227,6 +227,7 @@ int plan_create(apde_plan **out, const apde_plan_desc *d) {
     p->padl = 64;  // 512 B (fp64) of zero columns: vector alignment + left tile overhang
     p->pitch = ((p->padl + d->cols + 576 + 63) / 64) * 64;  // right overhang: two of the widest warp strips
     if (const char *v = getenv("APDE_RB_VARIANT")) p->variant = (v[0] == 'v' ? atoi(v + 1) : atoi(v)) ? 1 : 0;
+    p->lane_vectors = d->dtype_bytes == 8 ? 2 : 1;  // 4 columns per lane for both types (measured best)
     if (const char *v = getenv("APDE_LANE_VECTORS")) p->lane_vectors = atoi(v) == 2 ? 2 : 1;
     if (const char *v = getenv("APDE_ROW_BLOCK")) p->row_block = std::max(8, atoi(v));
     const size_t bytes = p->plane_elems() * (size_t)p->elem;
@@ -519,7 +520,7 @@ int solve_redblack(int elem, double *grid, const double *nh, const double *nv, c
         return APDE_OK;
     }
     if (check_every <= 0) check_every = 32;
-    if (temporal_depth <= 0) temporal_depth = 4;
+    if (temporal_depth <= 0) temporal_depth = nh ? 2 : 3;  // measured best fused depth per variant
     if (rows < 3 || cols < 3) {
         const int64_t n = (0.0 < tol) ? std::min<int64_t>(check_every, max_iter) : max_iter;
         for (int64_t k = 0; k < n; ++k) hist[k] = 0.0;

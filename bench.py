@@ -48,14 +48,17 @@ def parse_args():
     ap.add_argument("--rows", type=int, default=16384, help="rows per GPU")
     ap.add_argument("--cols", type=int, default=16384)
     ap.add_argument("--sweeps", type=int, default=32, help="sweeps per step")
-    ap.add_argument("--depth", type=int, default=int(os.environ.get("APDE_TEMPORAL_DEPTH", "4")))
+    ap.add_argument("--depth", type=int, default=int(os.environ.get("APDE_TEMPORAL_DEPTH", "0")), help="fused sweeps per HBM pass (0 = measured best: 3, or 2 with mismatch)")
     ap.add_argument("--noise", type=float, default=0.0, help="link mismatch sigma (0 = Poisson, no mismatch)")
     ap.add_argument("--no-source", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.depth <= 0:
+        args.depth = 2 if args.noise > 0 else 3
+    return args
 
 
 # ------------------------------------------------------------------------------------------------
@@ -151,7 +154,6 @@ def run_reference(args):
         if k >= args.warmup:
             vals.append(v)
     value = statistics.mean(vals)
-    n_lup = (4096 - 2) ** 2
     out = {
         "impl": "reference", "metric": "GLUP/s", "value": value, "unit": "GLUP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
