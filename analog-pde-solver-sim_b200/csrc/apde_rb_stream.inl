@@ -373,7 +373,7 @@ int RBS_FN(apde_plan *p, int64_t n_sweeps, int64_t sweep_base, int phase, cudaSt
         a.own_lo = g.own_lo;
         a.own_hi = g.own_hi;
         const long long owned = g.own_hi - g.own_lo;
-        a.rbh = p->row_block;
+        a.rbh = std::max<int64_t>(p->row_block, p->halo);  // an edge block must hold the rows the halo exchange sends
         const long long nblk = (owned + a.rbh - 1) / a.rbh;
         const int lane_cols = p->lane_vectors == 2 ? RBS_C2 : RBS_C1;
         const int HCA = ((2 * td + lane_cols - 1) / lane_cols) * lane_cols;

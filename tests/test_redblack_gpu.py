@@ -152,3 +152,49 @@ def test_plan_two_strips_equal_one_strip_bitwise():
         b.close()
         assert out.tobytes() == ref.tobytes()
         assert hist.tobytes() == ref_hist.tobytes()
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_three_strips_phased_overlap_protocol(dt, monkeypatch):
+    """The multi-GPU schedule of analog_pde_solver/strips.py on one GPU: per group, phase 1 (row blocks
+    next to a neighbour) -> halo copies out of the half-written buffer -> phase 2 (interior blocks).
+    Three plans stand in for three ranks; result must equal the single-strip run bit for bit."""
+    monkeypatch.setenv("APDE_ROW_BLOCK", "16")
+    rows, cols, depth = 230, 140, 3
+    groups = [3, 3, 2, 1]
+    g0, nh, nv, s = random_problem(rows, cols, 0.01, seed=13)
+    lib = _backend.load()
+    kw = dict(dtype=dt, has_noise=True, has_source=True, temporal_depth=depth)
+    with _backend.Plan(rows, cols, **kw) as whole:
+        whole.upload(g0, nh, nv, s)
+        base = 0
+        for n in groups:
+            whole.run(n, base)
+            base += n
+        ref = whole.download()
+        ref_hist = whole.residuals(0, sum(groups))
+    cuts = [0, 70, 150, rows]
+    plans = [_backend.Plan(rows, cols, cuts[k], cuts[k + 1], **kw) for k in range(3)]
+    for p in plans:
+        p.upload(g0, nh, nv, s)
+    base = 0
+    for n in groups:
+        for p in plans:
+            p.run(n, base, phase=1)
+        for k in range(2):  # neighbour pairs (k, k+1)
+            send_dn, recv_dn, nb = plans[k].halo(1)
+            send_up, recv_up, nb2 = plans[k + 1].halo(0)
+            assert nb == nb2
+            _backend.check(lib.apde_memcpy_dtod(recv_up, send_dn, nb, None))
+            _backend.check(lib.apde_memcpy_dtod(recv_dn, send_up, nb, None))
+        for p in plans:
+            p.run(n, base, phase=2)
+        base += n
+    out = np.zeros((rows, cols))
+    hist = np.zeros(sum(groups))
+    for p in plans:
+        p.download(out)
+        hist = np.maximum(hist, p.residuals(0, sum(groups)))
+        p.close()
+    assert out.tobytes() == ref.tobytes()
+    assert hist.tobytes() == ref_hist.tobytes()

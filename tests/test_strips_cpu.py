@@ -1,0 +1,127 @@
+"""CPU (gloo, world_size 2 and 3): host logic of the row-strip driver -- partitioning, sweep groups,
+halo exchange order, residual MAX all-reduce.  The sweep engine is a stand-in built on the test
+oracle (the product engine is CudaStripEngine -> libapde.so; tests/test_redblack_gpu.py and
+tests/test_strips_gpu.py cover it on the GPU).  The multi-rank result must equal the single-strip
+oracle bit for bit."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+from helpers import random_problem
+from analog_pde_solver.strips import StripSolver, partition_rows, sweep_groups
+
+
+class OracleStripEngine:
+    """Local strip with ghost rows, relaxed by the CPU oracle (test stand-in for a libapde plan)."""
+
+    def __init__(self, g0, nh, nv, src, row_begin, row_end, depth, dtype=np.float64):
+        grows, cols = g0.shape
+        self.halo = 2 * depth
+        self.gt = self.halo if row_begin > 0 else 0
+        self.gb = self.halo if row_end < grows else 0
+        lo, hi = row_begin - self.gt, row_end + self.gb
+        self.pad = lo & 1  # keep the oracle's local colour parity equal to the global one
+        sl = slice(lo - self.pad, hi)
+        self.u = np.ascontiguousarray(g0[sl]).astype(dtype)
+        self.nh = None if nh is None else np.ascontiguousarray(nh[sl])
+        self.nv = None if nv is None else np.ascontiguousarray(nv[lo - self.pad:hi - 1])
+        self.src = None if src is None else np.ascontiguousarray(src[sl])
+        self.own = slice(self.pad + self.gt, self.pad + self.gt + (row_end - row_begin))
+        self.dtype = dtype
+        self.resid = np.zeros(4096, dtype=np.float64)
+        self.calls = []
+
+    def run(self, n, base, phase=0):
+        self.calls.append((n, base, phase))
+        if phase == 2:
+            return
+        for s in range(n):
+            before = self.u.copy()
+            self.u, _, _ = oracle.red_black(self.u, self.nh, self.nv, self.src, 1, dtype=self.dtype)
+            ch = np.abs(self.u[self.own].astype(np.float64) - before[self.own].astype(np.float64))
+            ch = ch[~np.isnan(ch)]
+            self.resid[base + s] = ch.max() if ch.size else 0.0
+
+    def halo_tensors(self, side):
+        t = torch.from_numpy(self.u)
+        if side == 0 and self.gt:
+            a = self.pad
+            return t[a + self.gt:a + self.gt + self.halo], t[a:a + self.gt]
+        if side == 1 and self.gb:
+            e = self.own.stop
+            return t[e - self.halo:e], t[e:e + self.gb]
+        return None, None
+
+    def residual_tensor(self, first, count):
+        return torch.from_numpy(self.resid[first:first + count])
+
+    # the CPU stand-in has no streams
+    class _Null:
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+    def comm_scope(self):
+        return self._Null()
+
+    def join_comm(self):
+        pass
+
+
+def _worker(rank, world, port, rows, cols, depth, n_sweeps, overlap, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g0, nh, nv, src = random_problem(rows, cols, 0.01, seed=5)
+        begin, end = partition_rows(rows, world)[rank]
+        eng = OracleStripEngine(g0, nh, nv, src, begin, end, depth)
+        solver = StripSolver(eng, rank, world, depth, dist)
+        solver.run(n_sweeps, overlap=overlap)
+        res = solver.residuals(0, n_sweeps)
+        ref, ref_hist, _ = oracle.red_black(g0, nh, nv, src, n_sweeps)
+        ok_grid = eng.u[eng.own].tobytes() == ref[begin:end].tobytes()
+        ok_hist = res.tobytes() == ref_hist.tobytes()
+        out[rank] = (ok_grid, ok_hist, solver.exchanges, [c[2] for c in eng.calls])
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("world,rows,cols,depth,n_sweeps,overlap", [
+    (2, 40, 22, 2, 7, False), (2, 41, 19, 3, 6, True), (3, 60, 17, 2, 5, True)])
+def test_strips_equal_single_strip_bitwise(world, rows, cols, depth, n_sweeps, overlap):
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), rows, cols, depth, n_sweeps, overlap, out), nprocs=world, join=True)
+    assert len(out) == world
+    for rank in range(world):
+        ok_grid, ok_hist, exchanges, phases = out[rank]
+        assert ok_grid, f"rank {rank}: owned rows differ from the single-strip result"
+        assert ok_hist, f"rank {rank}: all-reduced residuals differ"
+        assert exchanges == len(sweep_groups(n_sweeps, depth))
+        assert set(phases) == ({1, 2} if overlap else {0})
+
+
+def test_partition_and_groups():
+    assert partition_rows(10, 3) == [(0, 4), (4, 7), (7, 10)]
+    assert partition_rows(16384 * 8, 8)[7] == (16384 * 7, 16384 * 8)
+    parts = partition_rows(65536, 8)
+    assert parts[0][0] == 0 and parts[-1][1] == 65536 and all(b - a == 8192 for a, b in parts)
+    assert sweep_groups(32, 3) == [3] * 10 + [2]
+    assert sweep_groups(4, 4) == [4] and sweep_groups(0, 4) == []
