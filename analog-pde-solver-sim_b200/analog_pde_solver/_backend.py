@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = (
     "apde_version", "apde_device_count", "apde_last_error",
     "apde_solve_exact_f64", "apde_solve_exact_f64_path", "apde_solve_redblack_f64", "apde_solve_redblack_f32",
     "apde_plan_create", "apde_plan_destroy", "apde_plan_upload", "apde_plan_upload_rows", "apde_plan_download_rows", "apde_plan_fill",
-    "apde_plan_download", "apde_plan_run", "apde_plan_halo", "apde_plan_residuals",
+    "apde_plan_download", "apde_plan_clear_residuals", "apde_plan_run", "apde_plan_halo", "apde_plan_residuals",
     "apde_plan_read_residuals", "apde_plan_launch_count", "apde_plan_checksum", "apde_memcpy_dtod",
 )
 
@@ -93,6 +93,8 @@ def load():
     lib.apde_plan_download.argtypes = [_vp, _dp]
     lib.apde_plan_run.restype = ctypes.c_int
     lib.apde_plan_run.argtypes = [_vp, _i64, _i64, ctypes.c_int, _vp]
+    lib.apde_plan_clear_residuals.restype = ctypes.c_int
+    lib.apde_plan_clear_residuals.argtypes = [_vp, _i64, _i64, _vp]
     lib.apde_plan_halo.restype = ctypes.c_int
     lib.apde_plan_halo.argtypes = [_vp, ctypes.c_int, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i64p]
     lib.apde_plan_residuals.restype = ctypes.c_int
@@ -215,6 +217,9 @@ class Plan:
 
     def run(self, n_sweeps: int, sweep_base: int = 0, phase: int = 0, stream: int = 0):
         check(self._lib.apde_plan_run(self._h, int(n_sweeps), int(sweep_base), int(phase), _vp(stream)))
+
+    def clear_residuals(self, first: int, count: int, stream: int = 0):
+        check(self._lib.apde_plan_clear_residuals(self._h, int(first), int(count), _vp(stream)))
 
     def halo(self, side: int):
         s, r, n = _vp(None), _vp(None), ctypes.c_int64(0)

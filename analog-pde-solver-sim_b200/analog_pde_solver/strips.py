@@ -61,6 +61,9 @@ class CudaStripEngine:
     def run(self, n_sweeps, sweep_base, phase=0):
         self.plan.run(n_sweeps, sweep_base, phase, self.stream())
 
+    def clear_residuals(self, first, count):
+        self.plan.clear_residuals(first, count, self.stream())
+
     def halo_tensors(self, side):
         send, recv, nbytes = self.plan.halo(side)
         if send is None:
@@ -82,7 +85,7 @@ class CudaStripEngine:
         main stream (the strip-edge row blocks), then carries the NCCL send/recv while the main
         stream runs the interior row blocks."""
         if not hasattr(self, "_comm_stream"):
-            self._comm_stream = self.torch.cuda.Stream()
+            self._comm_stream = self.torch.cuda.Stream(priority=-1)  # edge blocks + halo traffic go first
         self._comm_stream.wait_stream(self.torch.cuda.current_stream())
         return self.torch.cuda.stream(self._comm_stream)
 
@@ -126,10 +129,14 @@ class StripSolver:
         """Run n_sweeps sweeps (groups of <= temporal_depth, one exchange after each group)."""
         for n in sweep_groups(n_sweeps, self.depth):
             if overlap and self.world > 1:
-                self.engine.run(n, self.sweeps_done, phase=1)   # strip-edge row blocks first
+                # fork: the high-priority side stream relaxes the strip-edge row blocks and ships
+                # them to the neighbours while the main stream relaxes the interior row blocks;
+                # both read the same input buffer and write disjoint rows of the output buffer
+                self.engine.clear_residuals(self.sweeps_done, n)
                 with self.engine.comm_scope():
-                    self.exchange_halos()                       # overlaps the interior blocks
-                self.engine.run(n, self.sweeps_done, phase=2)   # interior row blocks
+                    self.engine.run(n, self.sweeps_done, phase=1)
+                    self.exchange_halos()
+                self.engine.run(n, self.sweeps_done, phase=2)
                 self.engine.join_comm()
             else:
                 self.engine.run(n, self.sweeps_done, phase=0)

@@ -153,6 +153,10 @@ int apde_plan_run(apde_plan *plan, int64_t n_sweeps, int64_t sweep_base, int pha
     return plan_run(plan, n_sweeps, sweep_base, phase, (cudaStream_t)stream);
 }
 
+int apde_plan_clear_residuals(apde_plan *plan, int64_t first, int64_t count, void *stream) {
+    return plan_clear_residuals(plan, first, count, (cudaStream_t)stream);
+}
+
 int apde_plan_halo(apde_plan *plan, int side, void **send_ptr, void **recv_ptr, int64_t *nbytes) {
     return plan_halo(plan, side, send_ptr, recv_ptr, nbytes);
 }

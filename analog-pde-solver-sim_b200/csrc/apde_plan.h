@@ -51,6 +51,7 @@ int plan_download(apde_plan *p, double *grid);
 int plan_upload_rows(apde_plan *p, int64_t win_lo, int64_t win_hi, const double *grid, const double *nh, const double *nv, const double *src);
 int plan_download_rows(apde_plan *p, int64_t win_lo, int64_t win_hi, double *out);
 int plan_run(apde_plan *p, int64_t n_sweeps, int64_t sweep_base, int phase, cudaStream_t st);
+int plan_clear_residuals(apde_plan *p, int64_t first, int64_t count, cudaStream_t st);
 int plan_halo(apde_plan *p, int side, void **send_ptr, void **recv_ptr, int64_t *nbytes);
 int plan_read_residuals(apde_plan *p, int64_t first, int64_t count, double *out, cudaStream_t st);
 int plan_checksum(apde_plan *p, double *sum_out, double *absmax_out, cudaStream_t st);

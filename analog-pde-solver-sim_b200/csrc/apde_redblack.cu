@@ -440,10 +440,27 @@ int plan_run(apde_plan *p, int64_t n_sweeps, int64_t sweep_base, int phase, cuda
         APDE_CUDA(cudaDeviceSynchronize());
         APDE_TRY(plan_ensure_resid(p, std::max<int64_t>(2 * p->resid_cap, sweep_base + n_sweeps)));
     }
-    if (phase != 2 && n_sweeps > 0)
+    // phase 0 zeroes its residual slots itself; phased runs put the two launches on different
+    // streams, so the caller clears the slots (apde_plan_clear_residuals) before forking
+    if (phase == 0 && n_sweeps > 0)
         APDE_CUDA(cudaMemsetAsync((char *)p->resid.p + (size_t)sweep_base * p->elem, 0, (size_t)n_sweeps * p->elem, st));
     return p->elem == 8 ? run_dispatch<double>(p, n_sweeps, sweep_base, phase, st)
                         : run_dispatch<float>(p, n_sweeps, sweep_base, phase, st);
+}
+
+int plan_clear_residuals(apde_plan *p, int64_t first, int64_t count, cudaStream_t st) {
+    if (!p || first < 0 || count < 0) {
+        set_error("plan_clear_residuals: bad argument");
+        return APDE_EINVAL;
+    }
+    APDE_CUDA(cudaSetDevice(p->device));
+    if (first + count > p->resid_cap) {
+        APDE_CUDA(cudaDeviceSynchronize());
+        APDE_TRY(plan_ensure_resid(p, std::max<int64_t>(2 * p->resid_cap, first + count)));
+    }
+    if (count > 0)
+        APDE_CUDA(cudaMemsetAsync((char *)p->resid.p + (size_t)first * p->elem, 0, (size_t)count * p->elem, st));
+    return APDE_OK;
 }
 
 int plan_halo(apde_plan *p, int side, void **send_ptr, void **recv_ptr, int64_t *nbytes) {

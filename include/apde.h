@@ -135,7 +135,10 @@ int apde_plan_download(apde_plan *plan, double *grid);
  * when the strip has neighbours (halo validity); single-strip plans accept any n_sweeps.
  * `phase`: 0 = whole strip, 1 = only the row blocks adjacent to neighbours (launch first, then
  * start the halo exchange), 2 = the remaining interior blocks.  Per-sweep max_change goes to the
- * device residual array at index sweep_base + s.  Asynchronous. */
+ * device residual array at index sweep_base + s (max-accumulated).  Phase 0 zeroes its slots first;
+ * for phased runs -- whose two launches may sit on different streams -- call
+ * apde_plan_clear_residuals on the stream both launches are ordered after.  Asynchronous. */
+int apde_plan_clear_residuals(apde_plan *plan, int64_t first, int64_t count, void *stream);
 int apde_plan_run(apde_plan *plan, int64_t n_sweeps, int64_t sweep_base, int phase, void *stream);
 
 /* After a group of sweeps: device pointers + byte counts of the rows to send to / receive from the

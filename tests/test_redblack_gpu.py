@@ -180,6 +180,7 @@ def test_three_strips_phased_overlap_protocol(dt, monkeypatch):
     base = 0
     for n in groups:
         for p in plans:
+            p.clear_residuals(base, n)
             p.run(n, base, phase=1)
         for k in range(2):  # neighbour pairs (k, k+1)
             send_dn, recv_dn, nb = plans[k].halo(1)

@@ -48,6 +48,9 @@ class OracleStripEngine:
             ch = ch[~np.isnan(ch)]
             self.resid[base + s] = ch.max() if ch.size else 0.0
 
+    def clear_residuals(self, first, count):
+        self.resid[first:first + count] = 0.0
+
     def halo_tensors(self, side):
         t = torch.from_numpy(self.u)
         if side == 0 and self.gt:
