@@ -23,6 +23,8 @@
 //                          CTA, CTAs chained in a ring by acquire/release progress counters
 //                          (CTA of sweep t trails CTA of sweep t-1 by one diagonal).
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "apde_common.h"
@@ -292,6 +294,129 @@ __global__ void __launch_bounds__(1024, 1) exact_ring_kernel(K2Params p) {
 }
 
 // ------------------------------------------------------------------------------------------
+// K2b: the same ring, restructured for latency.
+//   * the sweep's own previous diagonal (north/west operands) lives in shared memory, double
+//     buffered -- it never round-trips through L2;
+//   * south/east/old operands of diagonal d+1 (written by the predecessor CTA, read from L2) are
+//     requested right after diagonal d's node consumed its own, so the L2 latency overlaps the
+//     remaining nodes, the barrier and the next diagonal's shared-memory reads;
+//   * link/source rows (immutable) are prefetched into L1 two diagonals ahead;
+//   * progress flags are exchanged once per KB diagonals instead of every diagonal (the CTA of
+//     sweep t trails the CTA of sweep t-1 by KB+1 diagonals), so the acquire-poll and the
+//     release fence leave the per-diagonal critical path.
+// NPT = nodes per thread per diagonal (compile time), blockDim.x * NPT >= longest diagonal.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void prefetch_l1_line(const void *p) {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
+template <bool HAS_NOISE, bool HAS_SRC, int NPT>
+__global__ void __launch_bounds__(1024, 1) exact_ring2_kernel(K2Params p, int kb) {
+    extern __shared__ __align__(16) double sdiag[];  // 2 x SP doubles: this sweep's diagonal d-1 / d
+    const int rows = p.rows, cols = p.cols;
+    const long long P = p.P;
+    const int SP = rows + 2;
+    const int G = gridDim.x, c = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+    const int dmax = rows + cols - 4;
+    const long long ND = dmax - 1;
+    const int pred = (c + G - 1) % G;
+    __shared__ double red[32];
+    double *__restrict__ U = p.U;
+
+    long long m = 0;
+    for (long long t = c; t < p.n_sweeps; t += G, ++m) {
+        const long long mpred = (c == 0) ? m - 1 : m;
+        double mx = 0.0;
+        int cur = 0;  // sdiag[cur] holds diagonal d-1 of this sweep
+        // diagonal 1 = nodes (0,1) and (1,0): both on the fixed ring
+        if (tid == 0) sdiag[0] = __ldcg(U + P + 0);
+        if (tid == 1) sdiag[1] = __ldcg(U + P + 1);
+        double us[NPT], ue[NPT], old[NPT];
+        for (int d0 = 2; d0 <= dmax; d0 += kb) {
+            const int d1 = min(d0 + kb - 1, dmax);
+            if (t > 0 && tid == 0) {
+                // the predecessor sweep must be past diagonal d1+1 for the whole batch
+                const unsigned long long need = (unsigned long long)(mpred * ND + (long long)(min(d1 + 1, dmax) - 1));
+                const unsigned long long *flag = p.progress + (size_t)pred * 16;
+                while (ld_acquire_u64(flag) < need) {
+                }
+            }
+            __syncthreads();
+            {   // operands of the batch's first diagonal (latency exposed once per batch)
+                const int ilo = max(1, d0 - (cols - 2)), ihi = min(rows - 2, d0 - 1);
+                const double *dn = U + (long long)(d0 + 1) * P, *me = U + (long long)d0 * P;
+#pragma unroll
+                for (int e = 0; e < NPT; ++e) {
+                    const int i = ilo + tid + e * nthr;
+                    if (i <= ihi) {
+                        us[e] = __ldcg(dn + i + 1);
+                        ue[e] = __ldcg(dn + i);
+                        old[e] = __ldcg(me + i);
+                    }
+                }
+            }
+            for (int d = d0; d <= d1; ++d) {
+                const int ilo = max(1, d - (cols - 2)), ihi = min(rows - 2, d - 1);
+                const int lo_all = max(0, d - (cols - 1)), hi_all = min(rows - 1, d);
+                const double *sp = sdiag + cur * SP;
+                double *sn = sdiag + (cur ^ 1) * SP;
+                double *me = U + (long long)d * P;
+                const bool more = d < d1;
+                const int nlo = max(1, d + 1 - (cols - 2)), nhi = min(rows - 2, d);
+                const double *ndn = U + (long long)(d + 2) * P, *nme = U + (long long)(d + 1) * P;
+#pragma unroll
+                for (int e = 0; e < NPT; ++e) {
+                    const int i = ilo + tid + e * nthr;
+                    if (i <= ihi) {
+                        double ln = 1.0, ls = 1.0, lw = 1.0, le = 1.0, sv = 0.0;
+                        if (HAS_NOISE) {
+                            ln = __ldg(p.LV + (long long)(d - 1) * P + i - 1);
+                            lw = __ldg(p.LH + (long long)(d - 1) * P + i);
+                            ls = __ldg(p.LV + (long long)d * P + i);
+                            le = __ldg(p.LH + (long long)d * P + i);
+                            if (d + 2 <= dmax) {
+                                prefetch_l1_line(p.LV + (long long)(d + 2) * P + i);
+                                prefetch_l1_line(p.LH + (long long)(d + 2) * P + i);
+                            }
+                        }
+                        if (HAS_SRC) {
+                            sv = __ldg(p.S + (long long)d * P + i);
+                            if (d + 2 <= dmax) prefetch_l1_line(p.S + (long long)(d + 2) * P + i);
+                        }
+                        const double nw = relax_node<HAS_NOISE, HAS_SRC>(sp[i - 1], us[e], sp[i], ue[e], ln, ls, lw, le, sv);
+                        mx = max_ignore_nan(mx, fabs(__dsub_rn(nw, old[e])));
+                        sn[i] = nw;
+                        __stcg(me + i, nw);
+                    }
+                    // request the next diagonal's operands for this thread's slot e
+                    const int ni = nlo + tid + e * nthr;
+                    if (more && ni <= nhi) {
+                        us[e] = __ldcg(ndn + ni + 1);
+                        ue[e] = __ldcg(ndn + ni);
+                        old[e] = __ldcg(nme + ni);
+                    }
+                }
+                // ring nodes at both ends of diagonal d are operands of diagonal d+1
+                if (tid == nthr - 1 && lo_all < ilo) sn[lo_all] = __ldcg(me + lo_all);
+                if (tid == nthr - 2 && hi_all > ihi) sn[hi_all] = __ldcg(me + hi_all);
+                __syncthreads();
+                cur ^= 1;
+            }
+            if (tid == 0) st_release_u64(p.progress + (size_t)c * 16, (unsigned long long)(m * ND + (d1 - 1)));
+        }
+        mx = warp_max(mx);
+        if ((tid & 31) == 0) red[tid >> 5] = mx;
+        __syncthreads();
+        if (tid < 32) {
+            double v = (tid < (nthr + 31) / 32) ? red[tid] : 0.0;
+            v = warp_max(v);
+            if (tid == 0) p.hist[t] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // host drivers
 // ------------------------------------------------------------------------------------------
 template <typename K>
@@ -379,31 +504,76 @@ static int solve_small(double *grid, const double *nh, const double *nv, const d
     return APDE_OK;
 }
 
+struct RingCfg {
+    int block = 1024;
+    int npt = 0;       // 0 => K2 (generic kernel), else K2b with this many nodes per thread
+    int kb = 8;        // diagonals per progress exchange (K2b)
+    size_t smem = 0;
+    int grid_max = 0;  // co-resident CTAs
+};
+
 template <bool N, bool S>
-static int ring_launch(const K2Params &p, int grid, int block, cudaStream_t st) {
-    void *args[] = {(void *)&p};
-    APDE_CUDA(cudaLaunchCooperativeKernel((void *)exact_ring_kernel<N, S>, dim3(grid), dim3(block),
-                                          args, 0, st));
+static const void *ring_fn(int npt) {
+    switch (npt) {
+        case 0: return (const void *)exact_ring_kernel<N, S>;
+        case 1: return (const void *)exact_ring2_kernel<N, S, 1>;
+        case 2: return (const void *)exact_ring2_kernel<N, S, 2>;
+        case 4: return (const void *)exact_ring2_kernel<N, S, 4>;
+        default: return (const void *)exact_ring2_kernel<N, S, 8>;
+    }
+}
+static const void *ring_fn(bool noise, bool src, int npt) {
+    if (noise && src) return ring_fn<true, true>(npt);
+    if (noise) return ring_fn<true, false>(npt);
+    if (src) return ring_fn<false, true>(npt);
+    return ring_fn<false, false>(npt);
+}
+
+static int ring_dispatch(bool noise, bool src, const K2Params &p, const RingCfg &cfg, int grid, cudaStream_t st) {
+    const void *fn = ring_fn(noise, src, cfg.npt);
+    int kb = cfg.kb;
+    void *args2[] = {(void *)&p, (void *)&kb};
+    void *args1[] = {(void *)&p};
+    APDE_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(cfg.block), cfg.npt ? args2 : args1, cfg.smem, st));
     return APDE_OK;
 }
 
-static int ring_dispatch(bool noise, bool src, const K2Params &p, int grid, int block,
-                         cudaStream_t st) {
-    if (noise && src) return ring_launch<true, true>(p, grid, block, st);
-    if (noise) return ring_launch<true, false>(p, grid, block, st);
-    if (src) return ring_launch<false, true>(p, grid, block, st);
-    return ring_launch<false, false>(p, grid, block, st);
-}
-
-static int ring_occupancy(bool noise, bool src, int block, int *per_sm) {
-    if (noise && src)
-        APDE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, exact_ring_kernel<true, true>, block, 0));
-    else if (noise)
-        APDE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, exact_ring_kernel<true, false>, block, 0));
-    else if (src)
-        APDE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, exact_ring_kernel<false, true>, block, 0));
-    else
-        APDE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, exact_ring_kernel<false, false>, block, 0));
+// picks the kernel + launch shape; K2b whenever the longest diagonal fits 8 nodes/thread and the two
+// diagonal buffers fit shared memory, else the generic K2
+static int ring_configure(bool noise, bool src, int64_t rows, int64_t cols, const cudaDeviceProp &prop, RingCfg *cfg) {
+    const int64_t maxdiag = std::min(rows, cols) - 2;
+    const char *force = getenv("APDE_RING_KERNEL");  // "k2" forces the generic kernel (cross-check)
+    const size_t smem2 = (size_t)2 * (rows + 2) * sizeof(double);
+    const bool can2 = maxdiag <= 8 * 1024 && smem2 + 1024 <= (size_t)prop.sharedMemPerBlockOptin;
+    // measured on B200 at 4096^2: K2b 116 vs K2 85 GLUP/s without mismatch, 50 vs 54 with (the four
+    // IEEE divisions per node dominate there), so mismatch problems stay on K2 unless forced
+    bool want2 = !noise;
+    if (force && !strcmp(force, "k2")) want2 = false;
+    if (force && !strcmp(force, "k2b")) want2 = true;
+    if (can2 && want2) {
+        int block = 1024;
+        while (block > 128 && block / 2 >= maxdiag) block /= 2;
+        int npt = 1;
+        while ((int64_t)block * npt < maxdiag) npt *= 2;
+        cfg->block = block;
+        cfg->npt = npt;
+        cfg->smem = smem2;
+        if (const char *v = getenv("APDE_RING_BATCH")) cfg->kb = std::max(1, atoi(v));
+    } else {
+        cfg->block = maxdiag > 2048 ? 1024 : (maxdiag > 512 ? 512 : 256);
+        cfg->npt = 0;
+        cfg->smem = 0;
+    }
+    const void *fn = ring_fn(noise, src, cfg->npt);
+    if (cfg->smem > 48 * 1024)
+        APDE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg->smem));
+    int per_sm = 0;
+    APDE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, cfg->block, cfg->smem));
+    if (per_sm < 1) {
+        set_error("exact ring kernel cannot be resident (block=%d smem=%zu)", cfg->block, cfg->smem);
+        return APDE_ECUDA;
+    }
+    cfg->grid_max = per_sm * prop.multiProcessorCount;
     return APDE_OK;
 }
 
@@ -443,16 +613,9 @@ static int solve_ring(double *grid, const double *nh, const double *nv, const do
     APDE_CUDA(cudaGetLastError());
     APDE_TRY(d_hist.alloc((size_t)max_iter * 8));
 
-    // block size: longest diagonal decides; two resident CTAs per SM hide each other's latency
-    const int64_t maxdiag = std::min(rows, cols) - 2;
-    int block = maxdiag > 2048 ? 1024 : (maxdiag > 512 ? 512 : 256);
-    int per_sm = 0;
-    APDE_TRY(ring_occupancy(noise, has_src, block, &per_sm));
-    if (per_sm < 1) {
-        set_error("exact_ring_kernel cannot be resident (block=%d)", block);
-        return APDE_ECUDA;
-    }
-    const int gmax = per_sm * prop.multiProcessorCount;
+    RingCfg cfg;
+    APDE_TRY(ring_configure(noise, has_src, rows, cols, prop, &cfg));
+    const int gmax = cfg.grid_max;
     APDE_TRY(d_prog.alloc((size_t)gmax * 16 * 8));
 
     const bool may_stop = tol > 0.0;
@@ -461,7 +624,7 @@ static int solve_ring(double *grid, const double *nh, const double *nv, const do
     // sweeps per launch when convergence has to be checked: enough to amortise the pipeline
     // fill/drain (2 diagonals per in-flight sweep) against nd diagonals per sweep
     int64_t chunk_cap = gmax;
-    while (chunk_cap * 2 <= 4096 && 2 * (int64_t)gmax > nd && chunk_cap < 8 * (int64_t)gmax) chunk_cap *= 2;
+    while (chunk_cap < 8 * (int64_t)gmax && (int64_t)(cfg.kb + 1) * chunk_cap > nd) chunk_cap *= 2;
 
     EventPair ev;
     APDE_TRY(ev.init());
@@ -486,7 +649,7 @@ static int solve_ring(double *grid, const double *nh, const double *nv, const do
         p.hist = d_hist.as<double>() + done;
         p.n_sweeps = chunk;
         APDE_CUDA(cudaEventRecord(ev.a));
-        APDE_TRY(ring_dispatch(noise, has_src, p, g, block, 0));
+        APDE_TRY(ring_dispatch(noise, has_src, p, cfg, g, 0));
         APDE_CUDA(cudaEventRecord(ev.b));
         APDE_CUDA(cudaEventSynchronize(ev.b));
         float ms = 0.f;
@@ -508,7 +671,7 @@ static int solve_ring(double *grid, const double *nh, const double *nv, const do
                     APDE_CUDA(cudaMemsetAsync(d_prog.p, 0, d_prog.bytes, 0));
                     p.n_sweeps = stop + 1;
                     APDE_CUDA(cudaEventRecord(ev.a));
-                    APDE_TRY(ring_dispatch(noise, has_src, p, (int)std::min<int64_t>(stop + 1, gmax), block, 0));
+                    APDE_TRY(ring_dispatch(noise, has_src, p, cfg, (int)std::min<int64_t>(stop + 1, gmax), 0));
                     APDE_CUDA(cudaEventRecord(ev.b));
                     APDE_CUDA(cudaEventSynchronize(ev.b));
                     APDE_CUDA(cudaEventElapsedTime(&ms, ev.a, ev.b));

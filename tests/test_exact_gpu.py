@@ -64,8 +64,11 @@ def test_python_classes_reproduce_reference(golden, name):
     (33, 65, 0.01, True, 40), (65, 33, 0.0, True, 40), (70, 70, 0.03, False, 31),
     (257, 129, 0.01, True, 11), (300, 300, 0.0, False, 13), (513, 700, 0.01, True, 6),
 ])
-@pytest.mark.parametrize("path", ["auto", "ring"])
-def test_fixed_sweeps_vs_oracle(rows, cols, sigma, src, k, path):
+@pytest.mark.parametrize("path", ["auto", "ring", "ring-k2", "ring-k2b"])
+def test_fixed_sweeps_vs_oracle(rows, cols, sigma, src, k, path, monkeypatch):
+    if path.startswith("ring-"):  # both ring kernels on every shape (default picks one per problem)
+        monkeypatch.setenv("APDE_RING_KERNEL", path[5:])
+        path = "ring"
     g0, nh, nv, s = random_problem(rows, cols, sigma, seed=rows * 1000 + cols, with_source=src)
     ru, rh, rn = oracle.gauss_seidel(g0, nh, nv, s, 0.0, k)
     g = g0.copy()
@@ -75,9 +78,12 @@ def test_fixed_sweeps_vs_oracle(rows, cols, sigma, src, k, path):
     assert g.tobytes() == ru.tobytes()
 
 
-@pytest.mark.parametrize("path", ["small", "ring"])
+@pytest.mark.parametrize("path", ["small", "ring", "ring-k2", "ring-k2b"])
 @pytest.mark.parametrize("tol", [1e-3, 1e-5, 3e-7])
-def test_early_stop_at_first_crossing(path, tol):
+def test_early_stop_at_first_crossing(path, tol, monkeypatch):
+    if path.startswith("ring-"):
+        monkeypatch.setenv("APDE_RING_KERNEL", path[5:])
+        path = "ring"
     """Stops at the true first sweep with max_change < tol although later sweeps were already in
     flight (snapshot + replay)."""
     g0, nh, nv, s = random_problem(40, 36, 0.01, seed=77)
