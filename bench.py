@@ -41,8 +41,8 @@ BYTES_PER_LUP = {  # algorithmic bytes per lattice update, one sweep, perfect ne
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--rows", type=int, default=16384, help="rows per GPU")
@@ -72,7 +72,14 @@ class ClockSampler:
     def __init__(self, index: int):
         self.index = index
         self.proc = None
-        self.lines = []
+        self.lines = []   # (arrival time, csv line)
+        self.window = [None, None]
+
+    def mark_begin(self):
+        self.window[0] = time.time()
+
+    def mark_end(self):
+        self.window[1] = time.time()
 
     def start(self):
         try:
@@ -85,7 +92,7 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
     def stop(self):
         if self.proc is None:
@@ -93,7 +100,11 @@ class ClockSampler:
         self.proc.terminate()
         sm, smax, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        t0, t1 = self.window
+        inside = [ln for (ts, ln) in self.lines if t0 is None or (t0 <= ts <= (t1 or ts) + 0.15)]
+        if not inside:  # region shorter than one sampling period: take the samples around it
+            inside = [ln for (_, ln) in self.lines[-3:]]
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -214,12 +225,13 @@ def run_ours(args):
         solver.run(args.sweeps)
         return solver.residuals(first, args.sweeps)  # device->host read of the step's result
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler.mark_begin()
     l0 = eng.plan.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -227,6 +239,7 @@ def run_ours(args):
         res = step()
     ev1.record()
     barrier()
+    sampler.mark_end()
     ms = ev0.elapsed_time(ev1)
     launches = eng.plan.launches - l0
     clocks = sampler.stop() if rank == 0 else None
@@ -298,9 +311,17 @@ def run_ours(args):
         per_gpu_glups = glups / world
         achieved = per_gpu_glups * bpl  # GB/s of algorithmic bytes per GPU
         n_sweep_launches = max(launches, 1)
+        traffic = None
+        try:  # DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            key = f"{args.dtype}_d{args.depth}_noise{int(has_noise)}_src{int(has_src)}_{args.rows}x{args.cols}"
+            traffic = tr.get(key, {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_kind": peak_kind, "kernel": "rb_stream_kernel",
+                    "traffic": traffic, "peak_kind": peak_kind, "kernel": "rb_stream_kernel",
                     "algorithmic_bytes_per_lup": bpl,
+                    "algorithmic_bytes_per_launch": bpl * (args.rows - 2) * (args.cols - 2) * args.depth,
                     "avg_launch_ms": ms / n_sweep_launches,
                     "note": "algorithmic bytes = one read+write of u (+source/links) per sweep; the kernel fuses "
                             f"{args.depth} sweeps per HBM pass, so frac may exceed 1 while DRAM traffic (ncu, profiles/) stays below peak"}
