@@ -23,21 +23,39 @@ template <> struct Ar<float> {
     static __device__ __forceinline__ float abs(float a) { return fabsf(a); }
 };
 
+// The red-black node update, split so that the operand that arrives last in the streaming kernel's
+// stage pipeline (the south neighbour, produced by the previous stage of the same iteration) enters
+// through ONE fused multiply-add:
+//     mismatch   : t = gN*uN; t = fma(gW,uW,t); t = fma(gE,uE,t); t = t - src; tq = t*0.25;
+//                  new = fma(gS*0.25, uS, tq)
+//     no mismatch: tq = (((uN + uW) + uE) - src) * 0.25;   new = fma(uS, 0.25, tq)
+// Mathematically the reference's (n+s+w+e-src)/4 (solver.py:275 / :350-356); the association is the
+// throughput path's own (its iterates are compared with the red-black oracle, which uses the same tree).
+template <typename T, bool NOISE, bool SRC>
+__device__ __forceinline__ T rb_partial(T un, T uw, T ue, T gn, T gw, T ge, T sv) {
+    T t;
+    if (NOISE) {
+        t = Ar<T>::mul(gn, un);
+        t = Ar<T>::fma(gw, uw, t);
+        t = Ar<T>::fma(ge, ue, t);
+    } else {
+        t = Ar<T>::add(un, uw);
+        t = Ar<T>::add(t, ue);
+    }
+    if (SRC) t = Ar<T>::sub(t, sv);
+    return Ar<T>::mul(t, (T)0.25);
+}
+template <typename T, bool NOISE>
+__device__ __forceinline__ T rb_south_weight(T gs) {
+    return NOISE ? Ar<T>::mul(gs, (T)0.25) : (T)0.25;
+}
+template <typename T>
+__device__ __forceinline__ T rb_finish(T tq, T gsq, T us) {
+    return Ar<T>::fma(gsq, us, tq);
+}
 template <typename T, bool NOISE, bool SRC>
 __device__ __forceinline__ T rb_relax(T un, T us, T uw, T ue, T gn, T gs, T gw, T ge, T sv) {
-    T acc;
-    if (NOISE) {
-        acc = Ar<T>::mul(gn, un);
-        acc = Ar<T>::fma(gs, us, acc);
-        acc = Ar<T>::fma(gw, uw, acc);
-        acc = Ar<T>::fma(ge, ue, acc);
-    } else {
-        acc = Ar<T>::add(un, us);
-        acc = Ar<T>::add(acc, uw);
-        acc = Ar<T>::add(acc, ue);
-    }
-    if (SRC) acc = Ar<T>::sub(acc, sv);
-    return Ar<T>::mul(acc, (T)0.25);
+    return rb_finish<T>(rb_partial<T, NOISE, SRC>(un, uw, ue, gn, gw, ge, sv), rb_south_weight<T, NOISE>(gs), us);
 }
 
 struct Geo {

@@ -242,16 +242,15 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
                     }
                 };
                 static_for<0, LA>(fetch);
+                // Part 1 (no dependence between stages): shuffles and everything of the update except the
+                // south neighbour, which the previous stage of this iteration is about to produce.
+                T tq[NS][CH], gsq[NS][CH];
                 static_for<0, NS>([&](auto s_tag) {
                     constexpr int s = decltype(s_tag)::value;
                     if constexpr (s + LA < NS) fetch(std::integral_constant<int, s + LA>{});
-                    // stage s relaxes colour s&1 of row r-1-LAG*s; everything is predicated, no branches
                     const int p = (rr + 1 + (LAG - 1) * s) & 1;
                     const int si = (rr - 1 - LAG * s + 8 * NW) % NW;
-                    const int su = (si + NW - 1) % NW, sd = (si + 1) % NW;
-                    const bool act_s = (act >> (LAG * s)) & 1u;
-                    const bool cnt_s = (cnt >> (LAG * s)) & 1u;
-                    const unsigned okmask = act_s ? colmask : 0u;
+                    const int su = (si + NW - 1) % NW;
                     T edge;  // the one cross-lane operand of this stage-row
                     if (p == 0) edge = __shfl_up_sync(0xffffffffu, w[si][C - 1], 1);
                     else edge = __shfl_down_sync(0xffffffffu, w[si][0], 1);
@@ -267,8 +266,24 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
                             ge = o_ge[s][q >> 1];
                         }
                         if (SRC) sv = o_sv[s][q >> 1];
+                        tq[s][q >> 1] = rb_partial<T, NOISE, SRC>(w[su][q], lf, rt, gn, gw, ge, sv);
+                        gsq[s][q >> 1] = rb_south_weight<T, NOISE>(gs);
+                    }
+                });
+                // Part 2 (the serial chain): one fused multiply-add + select per stage.
+                static_for<0, NS>([&](auto s_tag) {
+                    constexpr int s = decltype(s_tag)::value;
+                    // stage s relaxes colour s&1 of row r-1-LAG*s; everything is predicated, no branches
+                    const int p = (rr + 1 + (LAG - 1) * s) & 1;
+                    const int si = (rr - 1 - LAG * s + 8 * NW) % NW;
+                    const int sd = (si + 1) % NW;
+                    const bool act_s = (act >> (LAG * s)) & 1u;
+                    const bool cnt_s = (cnt >> (LAG * s)) & 1u;
+                    const unsigned okmask = act_s ? colmask : 0u;
+#pragma unroll
+                    for (int q = p; q < C; q += 2) {
                         const T old = w[si][q];
-                        const T nw = rb_relax<T, NOISE, SRC>(w[su][q], w[sd][q], lf, rt, gn, gs, gw, ge, sv);
+                        const T nw = rb_finish<T>(tq[s][q >> 1], gsq[s][q >> 1], w[sd][q]);
                         const T keep = ((okmask >> q) & 1u) ? nw : old;
                         w[si][q] = keep;
                         const T ch = abs_bits(Ar<T>::sub(keep, old));

@@ -165,10 +165,13 @@ int64_t apde_oracle_gs_f64_mt(double *grid, const double *nh, const double *nv,
  * Colour 0 = (i + j) even is relaxed first, then colour 1, each from the
  * other colour's freshest values.  Per node, with g = 1/noise precomputed
  * in fp64 and rounded once to the working type (kernel K5):
- *     acc = gN*uN; acc = fma(gS,uS,acc); acc = fma(gW,uW,acc); acc = fma(gE,uE,acc)
- *   no mismatch (gh == gv == NULL):  acc = ((uN + uS) + uW) + uE   -- the
- *   reference tree of solver.py:350-356
- *     acc = acc - src ; new = acc * 0.25 ; change = |new - old|
+ *     t = gN*uN; t = fma(gW,uW,t); t = fma(gE,uE,t); t = t - src; tq = t*0.25;
+ *     new = fma(gS*0.25, uS, tq)
+ *   no mismatch (gh == gv == NULL):
+ *     tq = (((uN + uW) + uE) - src) * 0.25;  new = fma(uS, 0.25, tq)
+ *   (the south neighbour enters last, through one fused multiply-add: it is
+ *   the operand the streaming kernel's stage pipeline produces last)
+ *     change = |new - old|
  * max_change of a sweep = max over both colours (NaN ignored, as the
  * reference's strict '>' does, solver.py:277).
  * Runs exactly n_sweeps; hist[t] = max_change of sweep t.
@@ -184,19 +187,20 @@ int64_t apde_oracle_gs_f64_mt(double *grid, const double *nh, const double *nv,
                 for (; j < cols - 1; j += 2) {                                             \
                     T un = u[IDX(i - 1, j)], us = u[IDX(i + 1, j)];                        \
                     T uw = u[IDX(i, j - 1)], ue = u[IDX(i, j + 1)];                        \
-                    T acc;                                                                 \
+                    T tq, gsq;                                                             \
                     if (gh) {                                                              \
-                        acc = gv[IDX(i - 1, j)] * un;                                      \
-                        acc = FMA(gv[IDX(i, j)], us, acc);                                 \
-                        acc = FMA(gh[(size_t)i * hc + (j - 1)], uw, acc);                  \
-                        acc = FMA(gh[(size_t)i * hc + j], ue, acc);                        \
+                        tq = gv[IDX(i - 1, j)] * un;                                       \
+                        tq = FMA(gh[(size_t)i * hc + (j - 1)], uw, tq);                    \
+                        tq = FMA(gh[(size_t)i * hc + j], ue, tq);                          \
+                        gsq = gv[IDX(i, j)] * (T)0.25;                                     \
                     } else {                                                               \
-                        acc = un + us;                                                     \
-                        acc = acc + uw;                                                    \
-                        acc = acc + ue;                                                    \
+                        tq = un + uw;                                                      \
+                        tq = tq + ue;                                                      \
+                        gsq = (T)0.25;                                                     \
                     }                                                                      \
-                    if (src) acc = acc - src[IDX(i, j)];                                   \
-                    T nv_ = acc * (T)0.25;                                                 \
+                    if (src) tq = tq - src[IDX(i, j)];                                     \
+                    tq = tq * (T)0.25;                                                     \
+                    T nv_ = FMA(gsq, us, tq);                                              \
                     T ch = FABS(nv_ - u[IDX(i, j)]);                                       \
                     if (ch > max_change) max_change = ch;                                  \
                     u[IDX(i, j)] = nv_;                                                    \

@@ -73,7 +73,9 @@ def test_red_black_no_noise_matches_numpy_statement():
         for i in range(1, 8):
             for j in range(1, 13):
                 if (i + j) % 2 == colour:
-                    ref[i, j] = ((((ref[i - 1, j] + ref[i + 1, j]) + ref[i, j - 1]) + ref[i, j + 1]) - src[i, j]) * 0.25
+                    # fma(uS, 0.25, tq): 0.25*uS is exact, so the sum below rounds exactly once
+                    tq = (((ref[i - 1, j] + ref[i, j - 1]) + ref[i, j + 1]) - src[i, j]) * 0.25
+                    ref[i, j] = 0.25 * ref[i + 1, j] + tq
     got, hist, _ = oracle.red_black(u, None, None, src, 1)
     assert got.tobytes() == ref.tobytes()
     assert hist[0] == np.max(np.abs(ref - u))
