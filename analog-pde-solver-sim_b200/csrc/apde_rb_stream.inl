@@ -30,7 +30,10 @@ namespace {
 using T = RBS_T;
 
 constexpr int RBS_THREADS = 128;
-constexpr int RBS_PF = 2;  // rows prefetched ahead (kept even so the unroll period stays even)
+#ifndef RBS_PF_ROWS
+#define RBS_PF_ROWS 2
+#endif
+constexpr int RBS_PF = RBS_PF_ROWS;  // rows prefetched ahead (kept even so the unroll period stays even)
 #ifndef RBS_LAG
 #define RBS_LAG 1
 #endif
@@ -60,11 +63,14 @@ __device__ __forceinline__ void static_for(F &&f) {
     }
 }
 
-constexpr int RBS_OPF = 3;  // iterations an operand row is prefetched into L1 before its first use
+#ifndef RBS_OPF_ROWS
+#define RBS_OPF_ROWS 3
+#endif
+constexpr int RBS_OPF = RBS_OPF_ROWS;  // iterations an operand row is prefetched into L1 before its first use
 #ifndef RBS_L2PF
 #define RBS_L2PF 12
 #endif
-constexpr int L2PF = RBS_L2PF;  // rows ahead that are pulled from HBM into L2 (0 = off)
+constexpr int L2PF_ROWS = RBS_L2PF;  // rows ahead that are pulled from HBM into L2 (source-only kernels)
 // Resident blocks per SM the compiler must allow (caps registers).  Measured on B200 (tools/rb_sweep.py):
 // the fp32 source-only kernels gain from 12 warps/SM (168 registers, no spills); every other variant
 // loses more to spills than it gains from occupancy.
@@ -139,6 +145,10 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
     constexpr int HCA = ((NS + C - 1) / C) * C;  // column halo, lane aligned
     constexpr int VW = CW - 2 * HCA;       // columns a strip stores
     static_assert(VW > 0 && NW % 2 == 0, "bad tile");
+    // prefetch distances, measured per variant on B200 (tools/rb_sweep.py): with conductances the extra
+    // prefetch instructions cost more than they hide
+    constexpr int L2PF = NOISE ? 0 : L2PF_ROWS;
+    constexpr int OPF = NOISE ? RBS_OPF : 2 * RBS_OPF;
 
     const int lane = threadIdx.x & 31;
     const long long warp_id = (long long)blockIdx.x * (RBS_THREADS / 32) + (threadIdx.x >> 5);
@@ -184,7 +194,6 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
             for (int q = 0; q < C; ++q) w[k][q] = (T)0;
 #pragma unroll
         for (int k = 0; k < RBS_PF; ++k) {
-            const int r = rs + k;
             load_row<C>(w[k], pin + k * pitch);  // rows past either end are zero padding
         }
         unsigned act = 0, cnt = 0;  // bit s: the row stage s handles this iteration is relaxed / counted
@@ -215,10 +224,10 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
                         prefetch_l2(pgv + (long long)L2PF * pitch);
                     }
                 }
-                if (SRC) prefetch_l1(psrc + (long long)RBS_OPF * pitch);
+                if (SRC) prefetch_l1(psrc + (long long)OPF * pitch);
                 if (NOISE) {
-                    prefetch_l1(pgh + (long long)RBS_OPF * pitch);
-                    prefetch_l1(pgv + (long long)RBS_OPF * pitch);
+                    prefetch_l1(pgh + (long long)OPF * pitch);
+                    prefetch_l1(pgv + (long long)OPF * pitch);
                 }
                 constexpr int CH = (C + 1) / 2;
                 // operands of the first LA stages are fetched up front, the rest one stage ahead
