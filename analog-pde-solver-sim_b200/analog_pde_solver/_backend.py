@@ -29,7 +29,7 @@ EXPORTED_SYMBOLS = (
     "apde_solve_exact_f64", "apde_solve_exact_f64_path", "apde_solve_redblack_f64", "apde_solve_redblack_f32",
     "apde_plan_create", "apde_plan_destroy", "apde_plan_upload", "apde_plan_upload_rows", "apde_plan_download_rows", "apde_plan_fill",
     "apde_plan_download", "apde_plan_clear_residuals", "apde_plan_run", "apde_plan_halo", "apde_plan_residuals",
-    "apde_plan_read_residuals", "apde_plan_launch_count", "apde_plan_checksum", "apde_memcpy_dtod",
+    "apde_plan_read_residuals", "apde_plan_launch_count", "apde_plan_checksum", "apde_memcpy_dtod", "apde_selftest_division",
 )
 
 
@@ -105,6 +105,8 @@ def load():
     lib.apde_plan_launch_count.argtypes = [_vp]
     lib.apde_plan_checksum.restype = ctypes.c_int
     lib.apde_plan_checksum.argtypes = [_vp, _dp, _dp, _vp]
+    lib.apde_selftest_division.restype = ctypes.c_int
+    lib.apde_selftest_division.argtypes = [_i64, ctypes.c_uint64, _i64p]
     lib.apde_memcpy_dtod.restype = ctypes.c_int
     lib.apde_memcpy_dtod.argtypes = [_vp, _vp, _i64, _vp]
     _lib = lib

@@ -181,6 +181,14 @@ int apde_plan_checksum(apde_plan *plan, double *sum_out, double *abs_max_out, vo
     return plan_checksum(plan, sum_out, abs_max_out, (cudaStream_t)stream);
 }
 
+int apde_selftest_division(int64_t n, uint64_t seed, int64_t *mismatches) {
+    if (n < 0 || !mismatches) {
+        set_error("apde_selftest_division: bad argument");
+        return APDE_EINVAL;
+    }
+    return selftest_division(n, seed, mismatches);
+}
+
 int apde_memcpy_dtod(void *dst, const void *src, int64_t nbytes, void *stream) {
     if (!dst || !src || nbytes < 0) {
         set_error("apde_memcpy_dtod: bad argument");

@@ -32,23 +32,119 @@
 namespace apde {
 
 // ------------------------------------------------------------------------------------------
+// IEEE-exact division by a link value with a precomputed reciprocal.
+//
+// A link is stored as {b, y}: b = the reference's mismatch factor, y = RN(1/b) computed once at
+// upload (__drcp_rn, correctly rounded) or 0.0 when b is not "safe" (see link_reciprocal).
+// For |a| in [2^-700, 2^700]:
+//     q0 = RN(a*y)                 within 1.5 ulp of a/b (y has relative error <= 2^-53)
+//     r0 = fma(-q0, b, a)          exact (fits 53 bits, cannot underflow in the screened ranges)
+//     q1 = fma(r0, y, q0)          = RN(a/b + (r0/b)*eps): faithful
+//     r1 = fma(-q1, b, a)          exact
+//     q2 = fma(r1, y, q1)          = RN(a/b + (r1/b)*eps) = RN(a/b)   (Markstein's theorem: holds for a
+//                                  correctly rounded y unless b's significand is all ones -- screened)
+// i.e. 1 DMUL + 4 DFMA instead of the ~30-instruction general division.  Zero numerators give the
+// correctly signed zero; every other case (tiny/huge/NaN/Inf numerators, unscreened links) takes
+// the general IEEE division.  apde_selftest_division() compares both paths bit for bit on the GPU.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double link_reciprocal(double b) {
+    const unsigned hi = (unsigned)__double2hiint(b), lo = (unsigned)__double2loint(b);
+    const unsigned e = (hi >> 20) & 0x7ffu;                     // biased exponent
+    const bool all_ones = ((hi & 0xfffffu) == 0xfffffu) && (lo == 0xffffffffu);
+    const bool safe = (e - 923u) <= 200u && !all_ones;          // |b| in [2^-100, 2^100], finite, normal
+    return safe ? __drcp_rn(b) : 0.0;
+}
+
+__device__ __forceinline__ double exact_div(double a, double2 link) {
+    const double b = link.x, y = link.y;
+    if (y != 0.0) {
+        const unsigned hi = (unsigned)__double2hiint(a);
+        const unsigned e = (hi >> 20) & 0x7ffu;
+        if ((e - 323u) <= 1400u) {  // |a| in [2^-700, 2^700]
+            double q = __dmul_rn(a, y);
+            double r = __fma_rn(-q, b, a);
+            q = __fma_rn(r, y, q);
+            r = __fma_rn(-q, b, a);
+            return __fma_rn(r, y, q);
+        }
+        if (a == 0.0)  // +-0 / finite non-zero b
+            return __hiloint2double((int)((hi ^ (unsigned)__double2hiint(b)) & 0x80000000u), 0);
+    }
+    return __ddiv_rn(a, b);
+}
+
+// ------------------------------------------------------------------------------------------
 // the node update, shared by K1 and K2
 // ------------------------------------------------------------------------------------------
 template <bool HAS_NOISE, bool HAS_SRC>
 __device__ __forceinline__ double relax_node(double un, double us, double uw, double ue,
-                                             double ln, double ls, double lw, double le,
+                                             double2 ln, double2 ls, double2 lw, double2 le,
                                              double src) {
     if (HAS_NOISE) {
-        un = __ddiv_rn(un, ln);  // solver.py:269
-        us = __ddiv_rn(us, ls);  // :270
-        uw = __ddiv_rn(uw, lw);  // :271
-        ue = __ddiv_rn(ue, le);  // :272
+        un = exact_div(un, ln);  // solver.py:269
+        us = exact_div(us, ls);  // :270
+        uw = exact_div(uw, lw);  // :271
+        ue = exact_div(ue, le);  // :272
     }
     double acc = __dadd_rn(un, us);  // :275, left-associative
     acc = __dadd_rn(acc, uw);
     acc = __dadd_rn(acc, ue);
     if (HAS_SRC) acc = __dsub_rn(acc, src);
     return __dmul_rn(acc, 0.25);  // == /4.0 exactly
+}
+
+// {b} -> {b, RN(1/b) or 0}
+__global__ void make_links_kernel(const double *__restrict__ b, double2 *__restrict__ out, long long n) {
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n;
+         k += (long long)gridDim.x * blockDim.x) {
+        const double v = b[k];
+        out[k] = make_double2(v, link_reciprocal(v));
+    }
+}
+
+// self-test: exact_div vs the general division on pseudo-random and adversarial operands
+__global__ void division_selftest_kernel(long long n, unsigned long long seed, unsigned long long *mismatches) {
+    unsigned long long bad = 0;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n;
+         k += (long long)gridDim.x * blockDim.x) {
+        // splitmix64 stream
+        unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(2 * k + 1);
+        auto next = [&]() {
+            z += 0x9E3779B97F4A7C15ull;
+            unsigned long long x = z;
+            x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+            x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+            return x ^ (x >> 31);
+        };
+        const unsigned long long ra = next(), rb = next(), rc = next();
+        // denominator: random significand, with a share of near-all-ones / near-power-of-two patterns
+        unsigned long long sig = rb & 0xFFFFFFFFFFFFFull;
+        const unsigned mode = (unsigned)(rc & 15u);
+        if (mode == 0) sig = 0xFFFFFFFFFFFFFull - (rc >> 60);          // all ones and neighbours
+        if (mode == 1) sig = (rc >> 60);                                // 1.0 and neighbours
+        if (mode == 2) sig = 0xFFFFFFFFFFFFFull - ((rc >> 40) & 0xFFFFF);
+        long long eb = 1023 + (long long)((rc >> 8) % 5) - 2;           // 2^-2 .. 2^2
+        if (mode == 3) eb = 1023 + (long long)((rc >> 8) % 300) - 150;  // includes unscreened exponents
+        const unsigned long long sb = (rc >> 7) & 1ull;
+        const double b = __longlong_as_double((long long)((sb << 63) | ((unsigned long long)eb << 52) | sig));
+        // numerator: mostly mid-range, some tiny / huge / zero / subnormal / inf / nan
+        double a;
+        const unsigned ma = (unsigned)((rc >> 20) & 31u);
+        if (ma == 0) a = 0.0;
+        else if (ma == 1) a = -0.0;
+        else if (ma == 2) a = __longlong_as_double((long long)(ra & 0x800FFFFFFFFFFFFFull));  // subnormal
+        else if (ma == 3) a = __longlong_as_double((long long)ra);                              // any bits
+        else {
+            long long ea = 1023 + (long long)((ra >> 53) % 1500) - 750;
+            if (ma >= 8) ea = 1023 + (long long)((ra >> 53) % 40) - 20;
+            a = __longlong_as_double((long long)((ra & 0x800FFFFFFFFFFFFFull) | ((unsigned long long)ea << 52)));
+        }
+        const double2 link = make_double2(b, link_reciprocal(b));
+        const double fast = exact_div(a, link), ref = __ddiv_rn(a, b);
+        const bool same = (__double_as_longlong(fast) == __double_as_longlong(ref)) || (fast != fast && ref != ref);
+        if (!same) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
 }
 
 // ==========================================================================================
@@ -58,8 +154,8 @@ constexpr int K1_MAX_BATCH = 256;
 
 struct K1Params {
     double *grid;          // rows*cols row-major (in: BC + initial guess, out: solution)
-    const double *nh;      // rows*(cols-1) or null
-    const double *nv;      // (rows-1)*cols or null
+    const double2 *nh;     // rows*(cols-1) {b, 1/b} or null
+    const double2 *nv;     // (rows-1)*cols {b, 1/b} or null
     const double *src;     // rows*cols or null
     double *snapshot;      // rows*cols scratch (rollback state)
     double *hist;          // capacity max_iter
@@ -71,7 +167,7 @@ struct K1Params {
 };
 
 template <bool HAS_NOISE, bool HAS_SRC>
-__device__ __forceinline__ void k1_run_batch(double *u, const double *nh, const double *nv,
+__device__ __forceinline__ void k1_run_batch(double *u, const double2 *nh, const double2 *nv,
                                              const double *src, double *slots, int rows,
                                              int cols, int nb) {
     const int hw = (cols - 1) / 2;  // candidate columns per row and parity
@@ -90,7 +186,8 @@ __device__ __forceinline__ void k1_run_batch(double *u, const double *nh, const 
                 const int tt = (s - i - j) >> 1;  // sweep (relative to the batch) this node is in
                 if (tt < 0 || tt >= nb || (s - i - j) < 0) continue;
                 const int c = i * cols + j;
-                double ln = 1.0, ls = 1.0, lw = 1.0, le = 1.0, sv = 0.0;
+                double2 ln = {1.0, 1.0}, ls = ln, lw = ln, le = ln;
+                double sv = 0.0;
                 if (HAS_NOISE) {
                     ln = nv[c - cols];
                     ls = nv[c];
@@ -117,14 +214,15 @@ __global__ void __launch_bounds__(1024, 1) exact_small_kernel(K1Params p) {
     const int rows = p.rows, cols = p.cols;
     const int n = rows * cols;
     double *u = reinterpret_cast<double *>(smem_raw);
-    double *slots = u + n;
-    double *cur = slots + K1_MAX_BATCH;
-    double *nh = nullptr, *nv = nullptr, *src = nullptr;
+    double *slots = u + n + (n & 1);
+    double *cur = slots + K1_MAX_BATCH;  // (n + (n&1) + K1_MAX_BATCH) is even: cur stays 16-byte aligned
+    double2 *nh = nullptr, *nv = nullptr;
+    double *src = nullptr;
     if (HAS_NOISE) {
-        nh = cur;
-        cur += rows * (cols - 1);
-        nv = cur;
-        cur += (rows - 1) * cols;
+        nh = reinterpret_cast<double2 *>(cur);
+        cur += 2 * rows * (cols - 1);
+        nv = reinterpret_cast<double2 *>(cur);
+        cur += 2 * (rows - 1) * cols;
     }
     if (HAS_SRC) src = cur;
     __shared__ int sh_stop;  // -1: no stop in this batch, else index of first converged sweep
@@ -193,6 +291,17 @@ __global__ void __launch_bounds__(1024, 1) exact_small_kernel(K1Params p) {
 //     north link = LV[d-1][i-1], west link = LH[d-1][i], south link = LV[d][i], east link = LH[d][i]
 //   every access is unit-stride in i.
 // ==========================================================================================
+// links: row-major {b} -> diagonal-major {b, 1/b}
+__global__ void to_diag_links_kernel(const double *__restrict__ rm, double2 *__restrict__ dm, int rows,
+                                     int cols, int P) {
+    const long long n = (long long)rows * cols;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n;
+         k += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(k / cols), j = (int)(k - (long long)i * cols);
+        const double v = rm[k];
+        dm[(long long)(i + j) * P + i] = make_double2(v, link_reciprocal(v));
+    }
+}
 __global__ void to_diag_kernel(const double *__restrict__ rm, double *__restrict__ dm, int rows,
                                int cols, int P) {
     // rm is rows x cols row-major (its own dims); dm[(i+j)*P + i]
@@ -224,7 +333,8 @@ __device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned l
 
 struct K2Params {
     double *U;
-    const double *LH, *LV, *S;
+    const double2 *LH, *LV;
+    const double *S;
     double *hist;                   // this launch's first sweep
     unsigned long long *progress;   // one counter per CTA (stride 16 to keep them on separate lines)
     int rows, cols, P;
@@ -264,7 +374,8 @@ __global__ void __launch_bounds__(1024, 1) exact_ring_kernel(K2Params p) {
                 const double un = __ldcg(up + i - 1), uw = __ldcg(up + i);
                 const double us = __ldcg(dn + i + 1), ue = __ldcg(dn + i);
                 const double old = __ldcg(me + i);
-                double ln = 1.0, ls = 1.0, lw = 1.0, le = 1.0, sv = 0.0;
+                double2 ln = {1.0, 1.0}, ls = ln, lw = ln, le = ln;
+                double sv = 0.0;
                 if (HAS_NOISE) {
                     ln = __ldg(p.LV + (long long)(d - 1) * P + i - 1);
                     lw = __ldg(p.LH + (long long)(d - 1) * P + i);
@@ -368,7 +479,8 @@ __global__ void __launch_bounds__(1024, 1) exact_ring2_kernel(K2Params p, int kb
                 for (int e = 0; e < NPT; ++e) {
                     const int i = ilo + tid + e * nthr;
                     if (i <= ihi) {
-                        double ln = 1.0, ls = 1.0, lw = 1.0, le = 1.0, sv = 0.0;
+                        double2 ln = {1.0, 1.0}, ls = ln, lw = ln, le = ln;
+                        double sv = 0.0;
                         if (HAS_NOISE) {
                             ln = __ldg(p.LV + (long long)(d - 1) * P + i - 1);
                             lw = __ldg(p.LH + (long long)(d - 1) * P + i);
@@ -427,8 +539,8 @@ static int max_dyn_smem(K kernel, size_t bytes) {
 
 static size_t k1_smem_bytes(int64_t rows, int64_t cols, bool noise, bool src) {
     size_t n = (size_t)rows * cols;
-    size_t d = n + K1_MAX_BATCH;
-    if (noise) d += (size_t)rows * (cols - 1) + (size_t)(rows - 1) * cols;
+    size_t d = n + (n & 1) + K1_MAX_BATCH;  // keep the link arrays 16-byte aligned
+    if (noise) d += 2 * ((size_t)rows * (cols - 1) + (size_t)(rows - 1) * cols);
     if (src) d += n;
     return d * sizeof(double);
 }
@@ -445,10 +557,17 @@ static int solve_small(double *grid, const double *nh, const double *nv, const d
     APDE_TRY(d_iters.alloc(8));
     APDE_CUDA(cudaMemcpy(d_grid.p, grid, n * 8, cudaMemcpyHostToDevice));
     if (noise) {
-        APDE_TRY(d_nh.alloc((size_t)rows * (cols - 1) * 8));
-        APDE_TRY(d_nv.alloc((size_t)(rows - 1) * cols * 8));
-        APDE_CUDA(cudaMemcpy(d_nh.p, nh, (size_t)rows * (cols - 1) * 8, cudaMemcpyHostToDevice));
-        APDE_CUDA(cudaMemcpy(d_nv.p, nv, (size_t)(rows - 1) * cols * 8, cudaMemcpyHostToDevice));
+        const size_t nhn = (size_t)rows * (cols - 1), nvn = (size_t)(rows - 1) * cols;
+        DevBuf tmp;
+        APDE_TRY(tmp.alloc(std::max(nhn, nvn) * 8));
+        APDE_TRY(d_nh.alloc(nhn * 16));
+        APDE_TRY(d_nv.alloc(nvn * 16));
+        APDE_CUDA(cudaMemcpy(tmp.p, nh, nhn * 8, cudaMemcpyHostToDevice));
+        make_links_kernel<<<64, 256>>>(tmp.as<double>(), d_nh.as<double2>(), (long long)nhn);
+        APDE_CUDA(cudaMemcpy(tmp.p, nv, nvn * 8, cudaMemcpyHostToDevice));
+        make_links_kernel<<<64, 256>>>(tmp.as<double>(), d_nv.as<double2>(), (long long)nvn);
+        APDE_CUDA(cudaGetLastError());
+        APDE_CUDA(cudaDeviceSynchronize());
     }
     if (has_src) {
         APDE_TRY(d_src.alloc(n * 8));
@@ -456,8 +575,8 @@ static int solve_small(double *grid, const double *nh, const double *nv, const d
     }
     K1Params p;
     p.grid = d_grid.as<double>();
-    p.nh = d_nh.as<double>();
-    p.nv = d_nv.as<double>();
+    p.nh = d_nh.as<double2>();
+    p.nv = d_nv.as<double2>();
     p.src = d_src.as<double>();
     p.snapshot = d_snap.as<double>();
     p.hist = d_hist.as<double>();
@@ -594,15 +713,15 @@ static int solve_ring(double *grid, const double *nh, const double *nv, const do
     APDE_CUDA(cudaMemcpy(stage.p, grid, n * 8, cudaMemcpyHostToDevice));
     to_diag_kernel<<<tg, tb>>>(stage.as<double>(), U.as<double>(), (int)rows, (int)cols, P);
     if (noise) {
-        APDE_TRY(LH.alloc(dbytes));
-        APDE_TRY(LV.alloc(dbytes));
-        // pad with 1.0 bit patterns is unnecessary: only valid links are ever read
-        APDE_CUDA(cudaMemset(LH.p, 0, dbytes));
-        APDE_CUDA(cudaMemset(LV.p, 0, dbytes));
+        APDE_TRY(LH.alloc(2 * dbytes));
+        APDE_TRY(LV.alloc(2 * dbytes));
+        // only valid links are ever read; the rest stays zero
+        APDE_CUDA(cudaMemset(LH.p, 0, 2 * dbytes));
+        APDE_CUDA(cudaMemset(LV.p, 0, 2 * dbytes));
         APDE_CUDA(cudaMemcpy(stage.p, nh, (size_t)rows * (cols - 1) * 8, cudaMemcpyHostToDevice));
-        to_diag_kernel<<<tg, tb>>>(stage.as<double>(), LH.as<double>(), (int)rows, (int)cols - 1, P);
+        to_diag_links_kernel<<<tg, tb>>>(stage.as<double>(), LH.as<double2>(), (int)rows, (int)cols - 1, P);
         APDE_CUDA(cudaMemcpy(stage.p, nv, (size_t)(rows - 1) * cols * 8, cudaMemcpyHostToDevice));
-        to_diag_kernel<<<tg, tb>>>(stage.as<double>(), LV.as<double>(), (int)rows - 1, (int)cols, P);
+        to_diag_links_kernel<<<tg, tb>>>(stage.as<double>(), LV.as<double2>(), (int)rows - 1, (int)cols, P);
     }
     if (has_src) {
         APDE_TRY(S.alloc(dbytes));
@@ -631,8 +750,8 @@ static int solve_ring(double *grid, const double *nh, const double *nv, const do
     float total_ms = 0.f;
     K2Params p;
     p.U = U.as<double>();
-    p.LH = LH.as<double>();
-    p.LV = LV.as<double>();
+    p.LH = LH.as<double2>();
+    p.LV = LV.as<double2>();
     p.S = S.as<double>();
     p.progress = d_prog.as<unsigned long long>();
     p.rows = (int)rows;
@@ -690,6 +809,21 @@ static int solve_ring(double *grid, const double *nh, const double *nv, const do
     from_diag_kernel<<<tg, tb>>>(U.as<double>(), stage.as<double>(), (int)rows, (int)cols, P);
     APDE_CUDA(cudaGetLastError());
     APDE_CUDA(cudaMemcpy(grid, stage.p, n * 8, cudaMemcpyDeviceToHost));
+    return APDE_OK;
+}
+
+int selftest_division(int64_t n, uint64_t seed, int64_t *mismatches) {
+    cudaDeviceProp prop;
+    APDE_TRY(require_sm100(&prop));
+    DevBuf cnt;
+    APDE_TRY(cnt.alloc(8));
+    APDE_CUDA(cudaMemset(cnt.p, 0, 8));
+    division_selftest_kernel<<<prop.multiProcessorCount * 8, 256>>>((long long)n, (unsigned long long)seed,
+                                                                  cnt.as<unsigned long long>());
+    APDE_CUDA(cudaGetLastError());
+    unsigned long long h = 0;
+    APDE_CUDA(cudaMemcpy(&h, cnt.p, 8, cudaMemcpyDeviceToHost));
+    *mismatches = (int64_t)h;
     return APDE_OK;
 }
 

@@ -60,6 +60,7 @@ int solve_redblack(int elem, double *grid, const double *nh, const double *nv, c
                    int64_t rows, int64_t cols, double tol, int64_t max_iter, int check_every,
                    int temporal_depth, double *hist, int64_t *iters, double *ksec);
 // implemented in apde_exact.cu
+int selftest_division(int64_t n, uint64_t seed, int64_t *mismatches);
 int solve_exact_f64(double *grid, const double *nh, const double *nv, const double *src,
                     int64_t rows, int64_t cols, double tol, int64_t max_iter, double *hist,
                     int64_t *iters, double *ksec, int force_path);

@@ -154,6 +154,10 @@ int64_t apde_plan_launch_count(const apde_plan *plan);
 /* sum_j u[row, j] style checksum of owned rows (fp64 accumulate) for cheap cross-rank checks. */
 int apde_plan_checksum(apde_plan *plan, double *sum_out, double *abs_max_out, void *stream);
 
+/* Device self-test of the exact path's link division (precomputed-reciprocal sequence vs the general
+ * IEEE division) on n pseudo-random + adversarial operand pairs; *mismatches must come back 0. */
+int apde_selftest_division(int64_t n, uint64_t seed, int64_t *mismatches);
+
 /* Device-to-device copy on `stream` (same device or peer device, e.g. a neighbour strip's halo
  * rows when both plans live in one process).  Asynchronous. */
 int apde_memcpy_dtod(void *dst, const void *src, int64_t nbytes, void *stream);

@@ -175,3 +175,35 @@ def test_reference_properties_poisson_and_cross():
     assert f"{a20.energy_joules(em) * 1e12:.3f}" == "28.026"
     assert f"{d20.energy_joules(em) * 1e12:.3f}" == "1209600.000"
     assert f"{em.efficiency_ratio(a20.energy_joules(em), d20.energy_joules(em)):.1f}" == "43159.2"
+
+
+def test_link_division_fast_path_is_ieee_exact():
+    """The exact path divides by link values with a precomputed-reciprocal FMA sequence; the device
+    self-test compares it with the general IEEE division on 2^28 random + adversarial operand pairs
+    (all-ones / near-power-of-two significands, zeros, subnormals, huge, NaN/Inf)."""
+    import ctypes
+    lib = _backend.load()
+    for seed in (1, 2, 3):
+        bad = ctypes.c_int64(-1)
+        _backend.check(lib.apde_selftest_division(1 << 28, seed, ctypes.byref(bad)))
+        assert bad.value == 0
+
+
+def test_unsafe_links_take_the_general_division():
+    """Links outside the screened range (negative, tiny, huge, all-ones significand, zero -> inf/nan
+    results) still reproduce the reference bit for bit."""
+    rng = np.random.default_rng(3)
+    rows, cols = 24, 20
+    g0, nh, nv, s = random_problem(rows, cols, 0.3, seed=8)
+    nh[3, 4] = -0.75
+    nh[5, 6] = 1e-200
+    nv[7, 8] = 1e200
+    nv[2, 2] = np.nextafter(2.0, 0.0)       # significand all ones
+    nh[9, 9] = np.nextafter(1.0, 0.0)
+    g0[10, 10] = -0.0
+    g0[11, 3] = 5e-324
+    for path in ("small", "ring"):
+        ru, rh, rn = oracle.gauss_seidel(g0, nh, nv, s, 0.0, 12)
+        g = g0.copy()
+        hist, n, _ = _backend.solve("exact", g, nh, nv, s, 0.0, 12, exact_path=path)
+        assert g.tobytes() == ru.tobytes() and hist.tobytes() == rh.tobytes()
