@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--noise", type=float, default=0.0, help="link mismatch sigma (0 = Poisson, no mismatch)")
     ap.add_argument("--no-source", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-sweeps", type=int, default=256,
+                    help="sweeps per end-to-end call (SURVEY 8d config 4: fixed K = 256, check_every = 32)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -250,13 +252,30 @@ def run_ours(args):
     lups_step = (grows - 2) * (args.cols - 2) * args.sweeps
     glups = lups_step * args.steps / (ms * 1e-3) / 1e9
 
-    # ---- e2e: host buffers through the public strip API, copies inside the timed region ------------
+    # ---- single-sweep launches (no temporal blocking): the plain-HBM-roofline reading of the kernel ----
+    single = None
+    if world == 1:
+        n1 = 16
+        for _ in range(3):
+            eng.run(1, solver.sweeps_done)
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(n1):
+            eng.run(1, solver.sweeps_done)   # one launch = one sweep = one pass over HBM
+        s1.record()
+        torch.cuda.synchronize()
+        single = (grows - 2) * (args.cols - 2) * n1 / (s0.elapsed_time(s1) * 1e-3) / 1e9
+
+    # ---- e2e: HOST buffers through the reference-facing call, copies inside the timed region ---------
+    # N = 1: the C-ABI one-shot solve the Python classes make (apde_solve_redblack_f64/f32: upload,
+    #        K sweeps with a residual read-back every 32, download), host arrays in pinned memory.
+    # N > 1: the strip API (apde_plan_upload_rows / run + halo exchange / apde_plan_download_rows).
     e2e = None
     if not args.no_e2e:
+        K = args.e2e_sweeps
         owned = end - begin
         pin = lambda shape: torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy()  # noqa: E731
-        # the public upload call takes GLOBAL arrays and reads only this strip's rows; a view whose
-        # base is offset lets each rank hold only its own rows (+halo) in pinned memory
         lo = max(begin - 2 * args.depth, 0)
         hi = min(end + 2 * args.depth, grows)
         host_u = pin((hi - lo, args.cols))
@@ -269,21 +288,30 @@ def run_ours(args):
         if has_noise:
             host_nh = pin((hi - lo, args.cols - 1))
             host_nh[:] = 1.0
-            host_nv = pin((hi - lo, args.cols))
+            host_nv = pin((hi - lo - (1 if world == 1 else 0), args.cols))
             host_nv[:] = 1.0
-        out_host = pin((owned, args.cols))
         h2d = host_u.nbytes + (host_s.nbytes if has_src else 0) + (host_nh.nbytes + host_nv.nbytes if has_noise else 0)
-        d2h = out_host.nbytes + args.sweeps * 8
+        if world == 1:
+            mode = "redblack" if args.dtype == "f64" else "redblack32"
+            d2h = host_u.nbytes + K * 8
 
-        def e2e_step():
-            _backend.check(eng.plan._lib.apde_plan_upload_rows(
-                eng.plan._h, lo, hi, _backend._ptr(host_u), _backend._ptr(host_nh), _backend._ptr(host_nv),
-                _backend._ptr(host_s)))
-            first = solver.sweeps_done
-            solver.run(args.sweeps)
-            r = solver.residuals(first, args.sweeps)
-            _backend.check(eng.plan._lib.apde_plan_download_rows(eng.plan._h, begin, end, _backend._ptr(out_host)))
-            return r
+            def e2e_step():
+                _backend.solve(mode, host_u, host_nh, host_nv, host_s, 0.0, K, check_every=32,
+                               temporal_depth=args.depth)
+            api = f"apde_solve_redblack_{args.dtype} (one call = upload + {K} sweeps, residuals read back every 32 + download)"
+        else:
+            out_host = pin((owned, args.cols))
+            d2h = out_host.nbytes + K * 8
+
+            def e2e_step():
+                _backend.check(eng.plan._lib.apde_plan_upload_rows(
+                    eng.plan._h, lo, hi, _backend._ptr(host_u), _backend._ptr(host_nh), _backend._ptr(host_nv),
+                    _backend._ptr(host_s)))
+                first = solver.sweeps_done
+                solver.run(K)
+                solver.residuals(first, K)
+                _backend.check(eng.plan._lib.apde_plan_download_rows(eng.plan._h, begin, end, _backend._ptr(out_host)))
+            api = f"apde_plan_upload_rows + {K} sweeps with NCCL halo exchange + residual all-reduce + apde_plan_download_rows"
 
         e2e_step()
         barrier()
@@ -295,9 +323,9 @@ def run_ours(args):
         tw = torch.tensor([wall], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tw, op=dist.ReduceOp.MAX)
-        e2e = {"value": lups_step * args.e2e_steps / float(tw.item()) / 1e9, "unit": "GLUP/s",
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "note": "apde_plan_upload_rows + sweeps + residual read + apde_plan_download_rows from/to pinned host memory"}
+        e2e = {"value": (grows - 2) * (args.cols - 2) * K * args.e2e_steps / float(tw.item()) / 1e9, "unit": "GLUP/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "sweeps_per_call": K,
+               "note": api + ", host arrays in pinned memory"}
 
     if rank == 0:
         peaks = {}
@@ -323,6 +351,9 @@ def run_ours(args):
                     "algorithmic_bytes_per_lup": bpl,
                     "algorithmic_bytes_per_launch": bpl * (args.rows - 2) * (args.cols - 2) * args.depth,
                     "avg_launch_ms": ms / n_sweep_launches,
+                    "single_sweep_launches": None if single is None else {
+                        "glups": single, "achieved": single * bpl, "frac": single * bpl / peak,
+                        "note": "same kernel, one sweep per launch (no temporal blocking): every launch moves the algorithmic bytes through HBM"},
                     "note": "algorithmic bytes = one read+write of u (+source/links) per sweep; the kernel fuses "
                             f"{args.depth} sweeps per HBM pass, so frac may exceed 1 while DRAM traffic (ncu, profiles/) stays below peak"}
         out = {"metric": "GLUP/s", "value": glups, "unit": "GLUP/s", "n_gpus": world, "steps": args.steps,
