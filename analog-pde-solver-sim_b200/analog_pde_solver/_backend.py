@@ -26,10 +26,10 @@ ERROR_NAMES = {-1: "APDE_EINVAL", -2: "APDE_ENODEV", -3: "APDE_ECUDA", -4: "APDE
 # every symbol include/apde.h declares (tests check that the shared object exports each one)
 EXPORTED_SYMBOLS = (
     "apde_version", "apde_device_count", "apde_last_error",
-    "apde_solve_exact_f64", "apde_solve_exact_f64_path", "apde_solve_redblack_f64", "apde_solve_redblack_f32",
+    "apde_solve_exact_f64", "apde_solve_exact_f64_path", "apde_solve_redblack_f64", "apde_solve_redblack_f32", "apde_release_cache",
     "apde_plan_create", "apde_plan_destroy", "apde_plan_upload", "apde_plan_upload_rows", "apde_plan_download_rows", "apde_plan_fill",
     "apde_plan_download", "apde_plan_clear_residuals", "apde_plan_run", "apde_plan_halo", "apde_plan_residuals",
-    "apde_plan_read_residuals", "apde_plan_launch_count", "apde_plan_checksum", "apde_memcpy_dtod", "apde_selftest_division",
+    "apde_plan_read_residuals", "apde_plan_launch_count", "apde_plan_checksum", "apde_memcpy_dtod", "apde_selftest_division", "apde_plan_energy_sums",
 )
 
 
@@ -105,6 +105,8 @@ def load():
     lib.apde_plan_launch_count.argtypes = [_vp]
     lib.apde_plan_checksum.restype = ctypes.c_int
     lib.apde_plan_checksum.argtypes = [_vp, _dp, _dp, _vp]
+    lib.apde_plan_energy_sums.restype = ctypes.c_int
+    lib.apde_plan_energy_sums.argtypes = [_vp, _dp, _dp, _vp]
     lib.apde_selftest_division.restype = ctypes.c_int
     lib.apde_selftest_division.argtypes = [_i64, ctypes.c_uint64, _i64p]
     lib.apde_memcpy_dtod.restype = ctypes.c_int
@@ -237,6 +239,12 @@ class Plan:
         s, m = ctypes.c_double(0.0), ctypes.c_double(0.0)
         check(self._lib.apde_plan_checksum(self._h, ctypes.byref(s), ctypes.byref(m), _vp(stream)))
         return float(s.value), float(m.value)
+
+    def energy_sums(self, stream: int = 0):
+        """(sum of squared horizontal drops, sum of squared vertical drops) over this strip's links."""
+        h, v = ctypes.c_double(0.0), ctypes.c_double(0.0)
+        check(self._lib.apde_plan_energy_sums(self._h, ctypes.byref(h), ctypes.byref(v), _vp(stream)))
+        return float(h.value), float(v.value)
 
     @property
     def launches(self) -> int:

@@ -143,6 +143,17 @@ class StripSolver:
                 self.exchange_halos()
             self.sweeps_done += n
 
+    def analog_energy_joules(self, resistor_ohms: float = 10_000.0) -> float:
+        """EnergyModel.analog_energy_joules (upstream solver.py:70-97) without moving the grid off the
+        GPUs: per-strip sums of squared link drops, SUM all-reduce, same closing arithmetic."""
+        sum_h, sum_v = self.engine.plan.energy_sums(self.engine.stream())
+        if self.dist is not None and self.world > 1:
+            t = self.engine.torch.tensor([sum_h, sum_v], dtype=self.engine.torch.float64, device="cuda")
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+            sum_h, sum_v = (float(x) for x in t.tolist())
+        watts = sum_h / resistor_ohms + sum_v / resistor_ohms
+        return watts * (5.0 * resistor_ohms * 1e-12)
+
     def residuals(self, first: int, count: int) -> np.ndarray:
         """Global per-sweep max_change: MAX all-reduce of the ranks' device arrays."""
         t = self.engine.residual_tensor(first, count)

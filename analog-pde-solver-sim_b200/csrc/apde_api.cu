@@ -125,6 +125,12 @@ int apde_solve_redblack_f32(double *grid, const double *noise_h, const double *n
                           temporal_depth, residual_history, iterations_run, kernel_seconds);
 }
 
+int apde_release_cache(void) {
+    std::lock_guard<std::mutex> lock(g_solve_mutex);
+    release_cached_plan();
+    return APDE_OK;
+}
+
 int apde_plan_create(apde_plan **plan, const apde_plan_desc *desc) { return plan_create(plan, desc); }
 
 int apde_plan_destroy(apde_plan *plan) {
@@ -179,6 +185,10 @@ int64_t apde_plan_launch_count(const apde_plan *plan) { return plan ? plan->laun
 
 int apde_plan_checksum(apde_plan *plan, double *sum_out, double *abs_max_out, void *stream) {
     return plan_checksum(plan, sum_out, abs_max_out, (cudaStream_t)stream);
+}
+
+int apde_plan_energy_sums(apde_plan *plan, double *sum_dh2, double *sum_dv2, void *stream) {
+    return plan_energy_sums(plan, sum_dh2, sum_dv2, (cudaStream_t)stream);
 }
 
 int apde_selftest_division(int64_t n, uint64_t seed, int64_t *mismatches) {

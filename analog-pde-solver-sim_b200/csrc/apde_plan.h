@@ -54,8 +54,10 @@ int plan_run(apde_plan *p, int64_t n_sweeps, int64_t sweep_base, int phase, cuda
 int plan_clear_residuals(apde_plan *p, int64_t first, int64_t count, cudaStream_t st);
 int plan_halo(apde_plan *p, int side, void **send_ptr, void **recv_ptr, int64_t *nbytes);
 int plan_read_residuals(apde_plan *p, int64_t first, int64_t count, double *out, cudaStream_t st);
+int plan_energy_sums(apde_plan *p, double *sum_h2, double *sum_v2, cudaStream_t st);
 int plan_checksum(apde_plan *p, double *sum_out, double *absmax_out, cudaStream_t st);
 int plan_ensure_resid(apde_plan *p, int64_t cap);
+void release_cached_plan();
 int solve_redblack(int elem, double *grid, const double *nh, const double *nv, const double *src,
                    int64_t rows, int64_t cols, double tol, int64_t max_iter, int check_every,
                    int temporal_depth, double *hist, int64_t *iters, double *ksec);

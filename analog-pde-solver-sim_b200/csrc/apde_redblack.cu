@@ -14,7 +14,9 @@
 // updated (they are the global Dirichlet ring, or the outermost ghost row).
 #include <algorithm>
 #include <cmath>
+#include <chrono>
 #include <cstdlib>
+#include <cstring>
 #include <new>
 #include <vector>
 
@@ -170,6 +172,39 @@ __global__ void checksum_kernel(const T *__restrict__ u, Geo g, double *out /*[0
     if ((threadIdx.x & 31) == 0) {
         atomicAdd(out, s);
         atomic_max_nonneg(out + 1, m);
+    }
+}
+
+// sum of squared voltage drops over the links this strip owns: horizontal links of owned rows and
+// vertical links from an owned row to the row below it (owned or ghost) -- the two sums of
+// EnergyModel.analog_energy_joules (solver.py:85-92 upstream), accumulated in fp64
+template <typename T>
+__global__ void energy_kernel(const T *__restrict__ u, Geo g, double *out /*[0]=sum dh^2,[1]=sum dv^2*/) {
+    const long long n = (g.own_hi - g.own_lo) * g.cols;
+    double sh = 0.0, sv = 0.0;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n;
+         k += (long long)gridDim.x * blockDim.x) {
+        const long long r = k / g.cols, j = k - r * g.cols;
+        const long long li = g.own_lo + r, gi = g.row0 + li;
+        const long long c = li * g.pitch + g.padl + j;
+        const double v = (double)u[c];
+        if (j + 1 < g.cols) {
+            const double d = (double)u[c + 1] - v;
+            sh += d * d;
+        }
+        if (gi + 1 < g.grows) {
+            const double d = (double)u[c + g.pitch] - v;
+            sv += d * d;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sh += __shfl_xor_sync(0xffffffffu, sh, o);
+        sv += __shfl_xor_sync(0xffffffffu, sv, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(out, sh);
+        atomicAdd(out + 1, sv);
     }
 }
 
@@ -525,9 +560,41 @@ int plan_checksum(apde_plan *p, double *sum_out, double *absmax_out, cudaStream_
     return APDE_OK;
 }
 
+int plan_energy_sums(apde_plan *p, double *sum_h2, double *sum_v2, cudaStream_t st) {
+    if (!p || !sum_h2 || !sum_v2) {
+        set_error("plan_energy_sums: NULL argument");
+        return APDE_EINVAL;
+    }
+    APDE_CUDA(cudaSetDevice(p->device));
+    const Geo g = make_geo(p);
+    APDE_CUDA(cudaMemsetAsync(p->scratch.p, 0, 16, st));
+    if (p->elem == 8)
+        energy_kernel<double><<<p->sm_count * 4, 256, 0, st>>>(p->U<double>(p->cur), g, p->scratch.as<double>());
+    else
+        energy_kernel<float><<<p->sm_count * 4, 256, 0, st>>>(p->U<float>(p->cur), g, p->scratch.as<double>());
+    APDE_CUDA(cudaGetLastError());
+    p->launches++;
+    double h[2];
+    APDE_CUDA(cudaMemcpyAsync(h, p->scratch.p, 16, cudaMemcpyDeviceToHost, st));
+    APDE_CUDA(cudaStreamSynchronize(st));
+    *sum_h2 = h[0];
+    *sum_v2 = h[1];
+    return APDE_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // one-shot host-buffer solve
 // ------------------------------------------------------------------------------------------
+static apde_plan *g_cached_plan = nullptr;  // never destroyed at exit (the context may be gone by then)
+
+void release_cached_plan() {
+    if (g_cached_plan) {
+        cudaSetDevice(g_cached_plan->device);
+        delete g_cached_plan;
+        g_cached_plan = nullptr;
+    }
+}
+
 int solve_redblack(int elem, double *grid, const double *nh, const double *nv, const double *src,
                    int64_t rows, int64_t cols, double tol, int64_t max_iter, int check_every,
                    int temporal_depth, double *hist, int64_t *iters, double *ksec) {
@@ -553,13 +620,37 @@ int solve_redblack(int elem, double *grid, const double *nh, const double *nv, c
     d.cols = cols;
     d.row_begin = 0;
     d.row_end = rows;
+    const bool trace = getenv("APDE_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
+    // Workspace cache: the device arrays of the last one-shot solve are kept and reused when the next
+    // call has the same shape / type / operands (cudaMalloc + cudaFree of several GB cost 10-100 ms and
+    // vary a lot).  Callers are serialised by the solve mutex.  APDE_NO_PLAN_CACHE=1 disables it,
+    // apde_release_cache() frees it.
     apde_plan *p = nullptr;
-    APDE_TRY(plan_create(&p, &d));
+    const bool use_cache = getenv("APDE_NO_PLAN_CACHE") == nullptr;
+    int dev = 0;
+    APDE_CUDA(cudaGetDevice(&dev));
+    if (use_cache && g_cached_plan && g_cached_plan->device == dev &&
+        memcmp(&g_cached_plan->d, &d, sizeof(d)) == 0) {
+        p = g_cached_plan;
+        g_cached_plan = nullptr;
+    } else {
+        release_cached_plan();
+        APDE_TRY(plan_create(&p, &d));
+    }
+    const double t_created = now();
     struct Guard {
         apde_plan *p;
-        ~Guard() { delete p; }
-    } guard{p};
+        bool keep;
+        ~Guard() {
+            if (!p) return;
+            if (keep) g_cached_plan = p;
+            else delete p;
+        }
+    } guard{p, use_cache};
     APDE_TRY(plan_upload(p, grid, nh, nv, src));
+    const double t_uploaded = now();
     EventPair ev;
     APDE_TRY(ev.init());
     float total_ms = 0.f;
@@ -580,7 +671,13 @@ int solve_redblack(int elem, double *grid, const double *nh, const double *nv, c
     }
     *iters = done;
     if (ksec) *ksec = total_ms * 1e-3;
-    return plan_download(p, grid);
+    const double t_swept = now();
+    const int rc = plan_download(p, grid);
+    if (trace)
+        fprintf(stderr, "[apde] solve_redblack %lldx%lld: create %.1f ms, upload %.1f ms, %lld sweeps %.1f ms (kernels %.1f ms), download %.1f ms\n",
+                (long long)rows, (long long)cols, (t_created - t_begin) * 1e3, (t_uploaded - t_created) * 1e3,
+                (long long)done, (t_swept - t_uploaded) * 1e3, total_ms, (now() - t_swept) * 1e3);
+    return rc;
 }
 
 }  // namespace apde

@@ -317,9 +317,14 @@ def run_ours(args):
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
+            ts = time.perf_counter()
             e2e_step()
+            if os.environ.get("APDE_TRACE"):
+                print(f"[bench] e2e call {time.perf_counter() - ts:.3f} s", file=sys.stderr, flush=True)
         barrier()
         wall = time.perf_counter() - t0
+        if os.environ.get("APDE_TRACE"):
+            print(f"[bench] e2e wall {wall:.3f} s for {args.e2e_steps} calls", file=sys.stderr, flush=True)
         tw = torch.tensor([wall], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tw, op=dist.ReduceOp.MAX)

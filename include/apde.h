@@ -82,6 +82,10 @@ int apde_solve_redblack_f32(double *grid, const double *noise_h, const double *n
                             double *residual_history, int64_t *iterations_run,
                             double *kernel_seconds);
 
+/* The red-black one-shot solves keep their device workspace for the next call of the same shape
+ * (allocation of several GB costs 10-100 ms); this frees it.  APDE_NO_PLAN_CACHE=1 disables the cache. */
+int apde_release_cache(void);
+
 /* ------------------------------------------------------------------------------------------
  * Device-resident strip plans (benchmark scale and multi-GPU row strips).
  *
@@ -153,6 +157,12 @@ int apde_plan_read_residuals(apde_plan *plan, int64_t first, int64_t count, doub
 int64_t apde_plan_launch_count(const apde_plan *plan);
 /* sum_j u[row, j] style checksum of owned rows (fp64 accumulate) for cheap cross-rank checks. */
 int apde_plan_checksum(apde_plan *plan, double *sum_out, double *abs_max_out, void *stream);
+
+/* On-device pieces of EnergyModel.analog_energy_joules (solver.py:85-92): sum of squared voltage drops
+ * over the horizontal links of the owned rows and over the vertical links below each owned row (needs
+ * fresh ghost rows).  Sum the two outputs over all strips; energy = (sum_dh2/R + sum_dv2/R) * 5*R*1pF.
+ * fp64 accumulation in a different order than numpy: agrees to rounding, not bit for bit. */
+int apde_plan_energy_sums(apde_plan *plan, double *sum_dh2, double *sum_dv2, void *stream);
 
 /* Device self-test of the exact path's link division (precomputed-reciprocal sequence vs the general
  * IEEE division) on n pseudo-random + adversarial operand pairs; *mismatches must come back 0. */

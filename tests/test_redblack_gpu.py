@@ -199,3 +199,32 @@ def test_three_strips_phased_overlap_protocol(dt, monkeypatch):
         p.close()
     assert out.tobytes() == ref.tobytes()
     assert hist.tobytes() == ref_hist.tobytes()
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_device_energy_matches_energy_model(dt):
+    """apde_plan_energy_sums (two strips) vs EnergyModel.analog_energy_joules on the downloaded grid."""
+    from analog_pde_solver import EnergyModel
+    rows, cols = 120, 77
+    g0, nh, nv, s = random_problem(rows, cols, 0.01, seed=31)
+    kw = dict(dtype=dt, has_noise=True, has_source=True, temporal_depth=2)
+    lib = _backend.load()
+    a = _backend.Plan(rows, cols, 0, 50, **kw)
+    b = _backend.Plan(rows, cols, 50, rows, **kw)
+    for p in (a, b):
+        p.upload(g0, nh, nv, s)
+        p.run(2, 0)
+    sa, ra, n = a.halo(1)
+    sb, rb, _ = b.halo(0)
+    _backend.check(lib.apde_memcpy_dtod(rb, sa, n, None))
+    _backend.check(lib.apde_memcpy_dtod(ra, sb, n, None))
+    out = np.zeros((rows, cols))
+    a.download(out)
+    b.download(out)
+    (ha, va), (hb, vb) = a.energy_sums(), b.energy_sums()
+    a.close()
+    b.close()
+    em = EnergyModel()
+    want = em.analog_energy_joules(out)
+    got = ((ha + hb) / em.resistor_ohms + (va + vb) / em.resistor_ohms) * (5.0 * em.resistor_ohms * 1e-12)
+    assert abs(got - want) <= 1e-12 * abs(want)
