@@ -90,50 +90,39 @@ __device__ __forceinline__ double abs_bits(double x) {
 }
 __device__ __forceinline__ float abs_bits(float x) { return fabsf(x); }
 
+// 16-byte vector loads/stores typed as the element type: the values land directly in (and leave
+// directly from) the registers of the window -- no int->fp repacking moves that would make the warp
+// wait for the load right after issuing it.
+__device__ __forceinline__ void ld_vec16(double *w, const double *p) {
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(w[0]), "=d"(w[1]) : "l"(p));
+}
+__device__ __forceinline__ void ld_vec16(float *w, const float *p) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(w[0]), "=f"(w[1]), "=f"(w[2]), "=f"(w[3])
+                 : "l"(p));
+}
+__device__ __forceinline__ void st_vec16(double *p, const double *w) {
+    asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(w[0]), "d"(w[1]) : "memory");
+}
+__device__ __forceinline__ void st_vec16(float *p, const float *w) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(w[0]), "f"(w[1]),
+                 "f"(w[2]), "f"(w[3])
+                 : "memory");
+}
+
 template <int C>
 __device__ __forceinline__ void load_row(T (&w)[C], const T *p) {
-    constexpr int BYTES = C * (int)sizeof(T);
-    static_assert(BYTES % 16 == 0, "lane vector must be a multiple of 16 bytes");
+    constexpr int PER = 16 / (int)sizeof(T);
+    static_assert(C % PER == 0, "lane vector must be a multiple of 16 bytes");
 #pragma unroll
-    for (int k = 0; k < BYTES / 16; ++k) {
-        int4 v;
-        asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
-                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                     : "l"(reinterpret_cast<const int4 *>(p) + k));
-        if (sizeof(T) == 8) {
-            w[2 * k + 0] = (T)__hiloint2double(v.y, v.x);
-            w[2 * k + 1] = (T)__hiloint2double(v.w, v.z);
-        } else {
-            w[4 * k + 0] = (T)__int_as_float(v.x);
-            w[4 * k + 1] = (T)__int_as_float(v.y);
-            w[4 * k + 2] = (T)__int_as_float(v.z);
-            w[4 * k + 3] = (T)__int_as_float(v.w);
-        }
-    }
+    for (int k = 0; k < C / PER; ++k) ld_vec16(&w[k * PER], p + k * PER);
 }
 
 template <int C>
 __device__ __forceinline__ void store_row(T *p, const T (&w)[C]) {
-    constexpr int BYTES = C * (int)sizeof(T);
+    constexpr int PER = 16 / (int)sizeof(T);
 #pragma unroll
-    for (int k = 0; k < BYTES / 16; ++k) {
-        int4 v;
-        if (sizeof(T) == 8) {
-            v.x = __double2loint((double)w[2 * k + 0]);
-            v.y = __double2hiint((double)w[2 * k + 0]);
-            v.z = __double2loint((double)w[2 * k + 1]);
-            v.w = __double2hiint((double)w[2 * k + 1]);
-        } else {
-            v.x = __float_as_int((float)w[4 * k + 0]);
-            v.y = __float_as_int((float)w[4 * k + 1]);
-            v.z = __float_as_int((float)w[4 * k + 2]);
-            v.w = __float_as_int((float)w[4 * k + 3]);
-        }
-        asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(
-                         reinterpret_cast<int4 *>(p) + k),
-                     "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
-                     : "memory");
-    }
+    for (int k = 0; k < C / PER; ++k) st_vec16(p + k * PER, &w[k * PER]);
 }
 
 template <int C, int TD, bool NOISE, bool SRC>
@@ -196,6 +185,19 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
         for (int k = 0; k < RBS_PF; ++k) {
             load_row<C>(w[k], pin + k * pitch);  // rows past either end are zero padding
         }
+        // Source-only kernels carry the next iteration's source operands in registers: they are requested
+        // right after this iteration's part 1 consumed the current ones, so their L1/L2 latency overlaps
+        // the serial part and the stores instead of stalling the in-order warp at first use.
+        constexpr bool CARRY = false && SRC && !NOISE && (LAG == 1);  // measured: no gain (fp64), -10 % (fp32, spills)
+        constexpr int CHc = (C + 1) / 2;
+        T c_sv[CARRY ? NS : 1][CHc];
+        if (CARRY) {
+#pragma unroll
+            for (int s = 0; s < NS; ++s)
+#pragma unroll
+                for (int q = 1; q < C; q += 2)  // iteration rr = 0 relaxes column parity 1
+                    c_sv[s][q >> 1] = __ldg(psrc - (long long)s * pitch + q);
+        }
         unsigned act = 0, cnt = 0;  // bit s: the row stage s handles this iteration is relaxed / counted
         T mxl[TD];
 #pragma unroll
@@ -250,13 +252,13 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
                         }
                     }
                 };
-                static_for<0, LA>(fetch);
+                if (!CARRY) static_for<0, LA>(fetch);
                 // Part 1 (no dependence between stages): shuffles and everything of the update except the
                 // south neighbour, which the previous stage of this iteration is about to produce.
                 T tq[NS][CH], gsq[NS][CH];
                 static_for<0, NS>([&](auto s_tag) {
                     constexpr int s = decltype(s_tag)::value;
-                    if constexpr (s + LA < NS) fetch(std::integral_constant<int, s + LA>{});
+                    if constexpr (!CARRY && s + LA < NS) fetch(std::integral_constant<int, s + LA>{});
                     const int p = (rr + 1 + (LAG - 1) * s) & 1;
                     const int si = (rr - 1 - LAG * s + 8 * NW) % NW;
                     const int su = (si + NW - 1) % NW;
@@ -274,11 +276,19 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
                             gw = o_gw[s][q >> 1];
                             ge = o_ge[s][q >> 1];
                         }
-                        if (SRC) sv = o_sv[s][q >> 1];
+                        if (SRC) sv = CARRY ? c_sv[s][q >> 1] : o_sv[s][q >> 1];
                         tq[s][q >> 1] = rb_partial<T, NOISE, SRC>(w[su][q], lf, rt, gn, gw, ge, sv);
                         gsq[s][q >> 1] = rb_south_weight<T, NOISE>(gs);
                     }
                 });
+                if (CARRY) {
+                    // operands of iteration r+1: stage s relaxes row r-s, column parity flips
+#pragma unroll
+                    for (int s = 0; s < NS; ++s)
+#pragma unroll
+                        for (int q = rr & 1; q < C; q += 2)
+                            c_sv[s][q >> 1] = __ldg(psrc + (long long)(1 - s) * pitch + q);
+                }
                 // Part 2 (the serial chain): one fused multiply-add + select per stage.
                 static_for<0, NS>([&](auto s_tag) {
                     constexpr int s = decltype(s_tag)::value;
