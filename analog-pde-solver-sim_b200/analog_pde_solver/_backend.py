@@ -29,7 +29,7 @@ EXPORTED_SYMBOLS = (
     "apde_solve_exact_f64", "apde_solve_exact_f64_path", "apde_solve_redblack_f64", "apde_solve_redblack_f32", "apde_release_cache",
     "apde_plan_create", "apde_plan_destroy", "apde_plan_upload", "apde_plan_upload_rows", "apde_plan_download_rows", "apde_plan_fill",
     "apde_plan_download", "apde_plan_clear_residuals", "apde_plan_run", "apde_plan_halo", "apde_plan_residuals",
-    "apde_plan_read_residuals", "apde_plan_launch_count", "apde_plan_checksum", "apde_memcpy_dtod", "apde_selftest_division", "apde_plan_energy_sums",
+    "apde_plan_read_residuals", "apde_plan_launch_count", "apde_plan_checksum", "apde_plan_checksum_bits", "apde_memcpy_dtod", "apde_selftest_division", "apde_plan_energy_sums",
 )
 
 
@@ -105,6 +105,8 @@ def load():
     lib.apde_plan_launch_count.argtypes = [_vp]
     lib.apde_plan_checksum.restype = ctypes.c_int
     lib.apde_plan_checksum.argtypes = [_vp, _dp, _dp, _vp]
+    lib.apde_plan_checksum_bits.restype = ctypes.c_int
+    lib.apde_plan_checksum_bits.argtypes = [_vp, ctypes.POINTER(ctypes.c_uint64), _vp]
     lib.apde_plan_energy_sums.restype = ctypes.c_int
     lib.apde_plan_energy_sums.argtypes = [_vp, _dp, _dp, _vp]
     lib.apde_selftest_division.restype = ctypes.c_int
@@ -239,6 +241,11 @@ class Plan:
         s, m = ctypes.c_double(0.0), ctypes.c_double(0.0)
         check(self._lib.apde_plan_checksum(self._h, ctypes.byref(s), ctypes.byref(m), _vp(stream)))
         return float(s.value), float(m.value)
+
+    def checksum_bits(self, stream: int = 0) -> int:
+        v = ctypes.c_uint64(0)
+        check(self._lib.apde_plan_checksum_bits(self._h, ctypes.byref(v), _vp(stream)))
+        return int(v.value)
 
     def energy_sums(self, stream: int = 0):
         """(sum of squared horizontal drops, sum of squared vertical drops) over this strip's links."""

@@ -184,7 +184,14 @@ int apde_plan_read_residuals(apde_plan *plan, int64_t first, int64_t count, doub
 int64_t apde_plan_launch_count(const apde_plan *plan) { return plan ? plan->launches : 0; }
 
 int apde_plan_checksum(apde_plan *plan, double *sum_out, double *abs_max_out, void *stream) {
-    return plan_checksum(plan, sum_out, abs_max_out, (cudaStream_t)stream);
+    return plan_checksum(plan, sum_out, abs_max_out, nullptr, (cudaStream_t)stream);
+}
+int apde_plan_checksum_bits(apde_plan *plan, uint64_t *bits_out, void *stream) {
+    if (!bits_out) {
+        set_error("apde_plan_checksum_bits: NULL argument");
+        return APDE_EINVAL;
+    }
+    return plan_checksum(plan, nullptr, nullptr, bits_out, (cudaStream_t)stream);
 }
 
 int apde_plan_energy_sums(apde_plan *plan, double *sum_dh2, double *sum_dv2, void *stream) {

@@ -55,7 +55,7 @@ int plan_clear_residuals(apde_plan *p, int64_t first, int64_t count, cudaStream_
 int plan_halo(apde_plan *p, int side, void **send_ptr, void **recv_ptr, int64_t *nbytes);
 int plan_read_residuals(apde_plan *p, int64_t first, int64_t count, double *out, cudaStream_t st);
 int plan_energy_sums(apde_plan *p, double *sum_h2, double *sum_v2, cudaStream_t st);
-int plan_checksum(apde_plan *p, double *sum_out, double *absmax_out, cudaStream_t st);
+int plan_checksum(apde_plan *p, double *sum_out, double *absmax_out, uint64_t *bits_out, cudaStream_t st);
 int plan_ensure_resid(apde_plan *p, int64_t cap);
 void release_cached_plan();
 int solve_redblack(int elem, double *grid, const double *nh, const double *nv, const double *src,

@@ -156,22 +156,31 @@ __global__ void fill_kernel(T *__restrict__ u, T *__restrict__ src, T *__restric
 }
 
 template <typename T>
-__global__ void checksum_kernel(const T *__restrict__ u, Geo g, double *out /*[0]=sum,[1]=absmax*/) {
+__global__ void checksum_kernel(const T *__restrict__ u, Geo g, double *out /*[0]=sum,[1]=absmax,[2]=bit sum*/) {
     const long long n = (g.own_hi - g.own_lo) * g.cols;
     double s = 0.0, m = 0.0;
+    unsigned long long bits = 0;  // wrap-around sum of the bit patterns: order independent, hence bitwise reproducible
     for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n;
          k += (long long)gridDim.x * blockDim.x) {
         const long long r = k / g.cols, j = k - r * g.cols;
-        const double v = (double)u[(g.own_lo + r) * g.pitch + g.padl + j];
+        const T e = u[(g.own_lo + r) * g.pitch + g.padl + j];
+        const double v = (double)e;
         s += v;
         m = max_ignore_nan(m, fabs(v));
+        const unsigned long long b = sizeof(T) == 8 ? (unsigned long long)__double_as_longlong((double)e)
+                                                    : (unsigned long long)__float_as_uint((float)e);
+        bits += b * (unsigned long long)(2 * ((g.row0 + g.own_lo + r) * g.cols + j) + 1);  // position-weighted
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        bits += __shfl_xor_sync(0xffffffffu, bits, o);
+    }
     m = warp_max(m);
     if ((threadIdx.x & 31) == 0) {
         atomicAdd(out, s);
         atomic_max_nonneg(out + 1, m);
+        atomicAdd(reinterpret_cast<unsigned long long *>(out + 2), bits);
     }
 }
 
@@ -538,25 +547,26 @@ int plan_read_residuals(apde_plan *p, int64_t first, int64_t count, double *out,
     return APDE_OK;
 }
 
-int plan_checksum(apde_plan *p, double *sum_out, double *absmax_out, cudaStream_t st) {
+int plan_checksum(apde_plan *p, double *sum_out, double *absmax_out, uint64_t *bits_out, cudaStream_t st) {
     if (!p) {
         set_error("plan_checksum: NULL plan");
         return APDE_EINVAL;
     }
     APDE_CUDA(cudaSetDevice(p->device));
     const Geo g = make_geo(p);
-    APDE_CUDA(cudaMemsetAsync(p->scratch.p, 0, 16, st));
+    APDE_CUDA(cudaMemsetAsync(p->scratch.p, 0, 24, st));
     if (p->elem == 8)
         checksum_kernel<double><<<p->sm_count * 4, 256, 0, st>>>(p->U<double>(p->cur), g, p->scratch.as<double>());
     else
         checksum_kernel<float><<<p->sm_count * 4, 256, 0, st>>>(p->U<float>(p->cur), g, p->scratch.as<double>());
     APDE_CUDA(cudaGetLastError());
     p->launches++;
-    double h[2];
-    APDE_CUDA(cudaMemcpyAsync(h, p->scratch.p, 16, cudaMemcpyDeviceToHost, st));
+    double h[3];
+    APDE_CUDA(cudaMemcpyAsync(h, p->scratch.p, 24, cudaMemcpyDeviceToHost, st));
     APDE_CUDA(cudaStreamSynchronize(st));
     if (sum_out) *sum_out = h[0];
     if (absmax_out) *absmax_out = h[1];
+    if (bits_out) memcpy(bits_out, &h[2], 8);
     return APDE_OK;
 }
 

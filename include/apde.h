@@ -157,6 +157,10 @@ int apde_plan_read_residuals(apde_plan *plan, int64_t first, int64_t count, doub
 int64_t apde_plan_launch_count(const apde_plan *plan);
 /* sum_j u[row, j] style checksum of owned rows (fp64 accumulate) for cheap cross-rank checks. */
 int apde_plan_checksum(apde_plan *plan, double *sum_out, double *abs_max_out, void *stream);
+/* Order-independent 64-bit checksum of the owned rows: wrap-around sum of (bit pattern x odd weight of the
+ * global position).  Equal bits <=> (with overwhelming probability) equal grids; strips add up (mod 2^64)
+ * to the single-strip value, so full-size multi-GPU / multi-kernel runs can be compared without a download. */
+int apde_plan_checksum_bits(apde_plan *plan, uint64_t *bits_out, void *stream);
 
 /* On-device pieces of EnergyModel.analog_energy_joules (solver.py:85-92): sum of squared voltage drops
  * over the horizontal links of the owned rows and over the vertical links below each owned row (needs

@@ -207,3 +207,16 @@ def test_unsafe_links_take_the_general_division():
         g = g0.copy()
         hist, n, _ = _backend.solve("exact", g, nh, nv, s, 0.0, 12, exact_path=path)
         assert g.tobytes() == ru.tobytes() and hist.tobytes() == rh.tobytes()
+
+
+def test_config3_size_4096_mismatch_iterates():
+    """BASELINE config 3 at full size: 4096^2 Laplace, 1 % mismatch from numpy's seeded stream, K = 16
+    sweeps; every residual and the whole grid equal the (multi-threaded, bitwise-serial) CPU oracle."""
+    n, k = 4096, 16
+    s = AnalogPDESolver(rows=n, cols=n, noise_level=0.01, rng_seed=0)
+    g0 = np.zeros((n, n))
+    g0[0, :] = 1.0
+    ru, rh, _ = oracle.gauss_seidel_mt(g0, s._noise_h, s._noise_v, None, k)
+    g = g0.copy()
+    hist, it, _ = _backend.solve("exact", g, s._noise_h, s._noise_v, None, 0.0, k)
+    assert it == k and hist.tobytes() == rh.tobytes() and g.tobytes() == ru.tobytes()

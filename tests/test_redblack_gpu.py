@@ -228,3 +228,35 @@ def test_device_energy_matches_energy_model(dt):
     want = em.analog_energy_joules(out)
     got = ((ha + hb) / em.resistor_ohms + (va + vb) / em.resistor_ohms) * (5.0 * em.resistor_ohms * 1e-12)
     assert abs(got - want) <= 1e-12 * abs(want)
+
+
+def test_full_size_two_kernel_families_agree_bitwise(monkeypatch):
+    """BASELINE config 4 size (16384^2 Poisson, fp32 to keep it quick): the fused streaming kernel
+    (depth 3, then a depth-2 tail) and the per-colour in-place kernels are independent implementations;
+    after 8 sweeps their order-independent 64-bit grid checksums and every per-sweep residual agree."""
+    n, k = 16384, 8
+    sums = {}
+    for variant in ("v1", "v0"):
+        monkeypatch.setenv("APDE_RB_VARIANT", variant)
+        with _backend.Plan(n, n, dtype=np.float32, has_noise=False, has_source=True, temporal_depth=3) as p:
+            p.fill(kind=1, top_hot=True, seed=1)
+            p.run(k, 0)
+            sums[variant] = (p.checksum_bits(), p.residuals(0, k).tobytes(), p.checksum())
+    assert sums["v1"][0] == sums["v0"][0]
+    assert sums["v1"][1] == sums["v0"][1]
+    assert sums["v1"][2][1] == sums["v0"][2][1] and sums["v1"][2][1] > 0   # same |u|max, and something moved
+
+
+def test_strip_checksums_add_up_to_single_strip():
+    rows, cols = 300, 200
+    g0, nh, nv, s = random_problem(rows, cols, 0.01, seed=2)
+    kw = dict(dtype=np.float64, has_noise=True, has_source=True, temporal_depth=2)
+    with _backend.Plan(rows, cols, **kw) as w:
+        w.upload(g0, nh, nv, s)
+        whole = w.checksum_bits()
+    parts = 0
+    for a, b in ((0, 120), (120, 300)):
+        with _backend.Plan(rows, cols, a, b, **kw) as p:
+            p.upload(g0, nh, nv, s)
+            parts = (parts + p.checksum_bits()) % (1 << 64)
+    assert parts == whole
