@@ -659,14 +659,19 @@ static int ring_dispatch(bool noise, bool src, const K2Params &p, const RingCfg 
 
 // picks the kernel + launch shape; K2b whenever the longest diagonal fits 8 nodes/thread and the two
 // diagonal buffers fit shared memory, else the generic K2
-static int ring_configure(bool noise, bool src, int64_t rows, int64_t cols, const cudaDeviceProp &prop, RingCfg *cfg) {
+static int ring_configure(bool noise, bool src, int64_t rows, int64_t cols, int64_t sweeps_hint,
+                          const cudaDeviceProp &prop, RingCfg *cfg) {
     const int64_t maxdiag = std::min(rows, cols) - 2;
     const char *force = getenv("APDE_RING_KERNEL");  // "k2" forces the generic kernel (cross-check)
     const size_t smem2 = (size_t)2 * (rows + 2) * sizeof(double);
     const bool can2 = maxdiag <= 8 * 1024 && smem2 + 1024 <= (size_t)prop.sharedMemPerBlockOptin;
-    // measured on B200 at 4096^2: K2b 116 vs K2 85 GLUP/s without mismatch, 50 vs 54 with (the four
-    // IEEE divisions per node dominate there), so mismatch problems stay on K2 unless forced
-    bool want2 = !noise;
+    // Measured on B200 at 4096^2 (tools/exact_bench.py):
+    //   many sweeps in flight (> 1 per SM): K2 with 512-thread CTAs, two per SM -- one CTA's L2 round
+    //     trips overlap the other's arithmetic: 96 GLUP/s with mismatch, 178 without;
+    //   at most one sweep per SM: 1024-thread CTAs; K2b (116) beats K2 (85) without mismatch, K2 (54)
+    //     beats K2b (50) with it (the four divisions per node dominate there).
+    const bool many = sweeps_hint > prop.multiProcessorCount;
+    bool want2 = !noise && !many;
     if (force && !strcmp(force, "k2")) want2 = false;
     if (force && !strcmp(force, "k2b")) want2 = true;
     if (can2 && want2) {
@@ -679,7 +684,8 @@ static int ring_configure(bool noise, bool src, int64_t rows, int64_t cols, cons
         cfg->smem = smem2;
         if (const char *v = getenv("APDE_RING_BATCH")) cfg->kb = std::max(1, atoi(v));
     } else {
-        cfg->block = maxdiag > 2048 ? 1024 : (maxdiag > 512 ? 512 : 256);
+        cfg->block = maxdiag > 2048 ? (many ? 512 : 1024) : (maxdiag > 512 ? 512 : 256);
+        if (const char *v = getenv("APDE_RING_BLOCK")) cfg->block = std::min(1024, std::max(64, atoi(v) / 32 * 32));
         cfg->npt = 0;
         cfg->smem = 0;
     }
@@ -733,7 +739,7 @@ static int solve_ring(double *grid, const double *nh, const double *nv, const do
     APDE_TRY(d_hist.alloc((size_t)max_iter * 8));
 
     RingCfg cfg;
-    APDE_TRY(ring_configure(noise, has_src, rows, cols, prop, &cfg));
+    APDE_TRY(ring_configure(noise, has_src, rows, cols, max_iter, prop, &cfg));
     const int gmax = cfg.grid_max;
     APDE_TRY(d_prog.alloc((size_t)gmax * 16 * 8));
 
