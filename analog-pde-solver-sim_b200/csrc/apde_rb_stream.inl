@@ -185,19 +185,6 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
         for (int k = 0; k < RBS_PF; ++k) {
             load_row<C>(w[k], pin + k * pitch);  // rows past either end are zero padding
         }
-        // Source-only kernels carry the next iteration's source operands in registers: they are requested
-        // right after this iteration's part 1 consumed the current ones, so their L1/L2 latency overlaps
-        // the serial part and the stores instead of stalling the in-order warp at first use.
-        constexpr bool CARRY = false && SRC && !NOISE && (LAG == 1);  // measured: no gain (fp64), -10 % (fp32, spills)
-        constexpr int CHc = (C + 1) / 2;
-        T c_sv[CARRY ? NS : 1][CHc];
-        if (CARRY) {
-#pragma unroll
-            for (int s = 0; s < NS; ++s)
-#pragma unroll
-                for (int q = 1; q < C; q += 2)  // iteration rr = 0 relaxes column parity 1
-                    c_sv[s][q >> 1] = __ldg(psrc - (long long)s * pitch + q);
-        }
         unsigned act = 0, cnt = 0;  // bit s: the row stage s handles this iteration is relaxed / counted
         T mxl[TD];
 #pragma unroll
@@ -252,13 +239,13 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
                         }
                     }
                 };
-                if (!CARRY) static_for<0, LA>(fetch);
+                static_for<0, LA>(fetch);
                 // Part 1 (no dependence between stages): shuffles and everything of the update except the
                 // south neighbour, which the previous stage of this iteration is about to produce.
                 T tq[NS][CH], gsq[NS][CH];
                 static_for<0, NS>([&](auto s_tag) {
                     constexpr int s = decltype(s_tag)::value;
-                    if constexpr (!CARRY && s + LA < NS) fetch(std::integral_constant<int, s + LA>{});
+                    if constexpr (s + LA < NS) fetch(std::integral_constant<int, s + LA>{});
                     const int p = (rr + 1 + (LAG - 1) * s) & 1;
                     const int si = (rr - 1 - LAG * s + 8 * NW) % NW;
                     const int su = (si + NW - 1) % NW;
@@ -276,19 +263,11 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
                             gw = o_gw[s][q >> 1];
                             ge = o_ge[s][q >> 1];
                         }
-                        if (SRC) sv = CARRY ? c_sv[s][q >> 1] : o_sv[s][q >> 1];
+                        if (SRC) sv = o_sv[s][q >> 1];
                         tq[s][q >> 1] = rb_partial<T, NOISE, SRC>(w[su][q], lf, rt, gn, gw, ge, sv);
                         gsq[s][q >> 1] = rb_south_weight<T, NOISE>(gs);
                     }
                 });
-                if (CARRY) {
-                    // operands of iteration r+1: stage s relaxes row r-s, column parity flips
-#pragma unroll
-                    for (int s = 0; s < NS; ++s)
-#pragma unroll
-                        for (int q = rr & 1; q < C; q += 2)
-                            c_sv[s][q >> 1] = __ldg(psrc + (long long)(1 - s) * pitch + q);
-                }
                 // Part 2 (the serial chain): one fused multiply-add + select per stage.
                 static_for<0, NS>([&](auto s_tag) {
                     constexpr int s = decltype(s_tag)::value;
