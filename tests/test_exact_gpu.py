@@ -220,3 +220,21 @@ def test_config3_size_4096_mismatch_iterates():
     g = g0.copy()
     hist, it, _ = _backend.solve("exact", g, s._noise_h, s._noise_v, None, 0.0, k)
     assert it == k and hist.tobytes() == rh.tobytes() and g.tobytes() == ru.tobytes()
+
+
+def test_poisson_demo_numbers():
+    """What examples/poisson_demo.py upstream prints (20 x 20) and BASELINE config 2 (64 x 64)."""
+    from helpers import zero_boundary, sin_source
+    for n, iters, err in ((20, 458, "2.2625e-03"), (64, 4070, "1.6709e-04")):
+        x = np.arange(n) / (n - 1)
+        exact = np.array([[np.sin(np.pi * i / (n - 1)) * np.sin(np.pi * j / (n - 1)) for j in range(n)] for i in range(n)])
+        a, d = AnalogPDESolver(rows=n, cols=n), DigitalSolver(rows=n, cols=n)
+        ua = a.solve(zero_boundary, source_fn=sin_source, tol=1e-7)
+        ud = d.solve(zero_boundary, source_fn=sin_source, tol=1e-7)
+        assert a.iterations_run == d.iterations_run == iters
+        assert f"{np.max(np.abs(ua - exact)):.4e}" == err and f"{np.max(np.abs(ud - exact)):.4e}" == err
+        if n == 20:
+            em = EnergyModel()
+            ea, ed = a.energy_joules(em), d.energy_joules(em)
+            assert f"{ea * 1e12:.3f}" == "24.730" and f"{ed * 1e12:.3f}" == "1648800.000"
+            assert f"{em.efficiency_ratio(ea, ed):.1f}" == "66671.7"
