@@ -29,7 +29,10 @@ namespace {
 
 using T = RBS_T;
 
-constexpr int RBS_THREADS = 128;
+#ifndef RBS_BLOCK
+#define RBS_BLOCK 128
+#endif
+constexpr int RBS_THREADS = RBS_BLOCK;  // no block-level cooperation: any multiple of 32 works
 #ifndef RBS_PF_ROWS
 #define RBS_PF_ROWS 2
 #endif
@@ -203,7 +206,7 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
                 // Operand rows (source / conductances) are pulled into L1 RBS_OPF iterations before
                 // their first use, then every stage's operands are loaded at the top of the
                 // iteration (L1 hits) so the loads overlap the dependent stage chain.
-                if (L2PF > 0) {
+                if (L2PF > 0 && r + L2PF <= re) {  // not past the item's last row (another warp's block)
                     // two-level software prefetch: HBM -> L2 far ahead (hides DRAM latency at low
                     // occupancy), L2 -> L1 / registers a few rows ahead
                     prefetch_l2(pin + (long long)L2PF * pitch);
