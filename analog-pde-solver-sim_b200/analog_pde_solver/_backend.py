@@ -26,7 +26,7 @@ ERROR_NAMES = {-1: "APDE_EINVAL", -2: "APDE_ENODEV", -3: "APDE_ECUDA", -4: "APDE
 # every symbol include/apde.h declares (tests check that the shared object exports each one)
 EXPORTED_SYMBOLS = (
     "apde_version", "apde_device_count", "apde_last_error",
-    "apde_solve_exact_f64", "apde_solve_exact_f64_path", "apde_solve_redblack_f64", "apde_solve_redblack_f32", "apde_release_cache",
+    "apde_solve_exact_f64", "apde_solve_exact_f64_path", "apde_solve_redblack_f64", "apde_solve_redblack_f32", "apde_solve_redblack_multi", "apde_release_cache",
     "apde_plan_create", "apde_plan_destroy", "apde_plan_upload", "apde_plan_upload_rows", "apde_plan_download_rows", "apde_plan_fill",
     "apde_plan_download", "apde_plan_clear_residuals", "apde_plan_run", "apde_plan_halo", "apde_plan_residuals",
     "apde_plan_read_residuals", "apde_plan_launch_count", "apde_plan_checksum", "apde_plan_checksum_bits", "apde_memcpy_dtod", "apde_selftest_division", "apde_plan_energy_sums",
@@ -77,6 +77,9 @@ def load():
         fn = getattr(lib, name)
         fn.restype = ctypes.c_int
         fn.argtypes = [_dp, _dp, _dp, _dp] + solve_tail + [ctypes.c_int, ctypes.c_int, _dp, _i64p, _dp]
+    lib.apde_solve_redblack_multi.restype = ctypes.c_int
+    lib.apde_solve_redblack_multi.argtypes = [ctypes.c_int, _dp, _dp, _dp, _dp] + solve_tail + [
+        ctypes.c_int, ctypes.c_int, ctypes.c_int, _dp, _i64p, _dp]
     lib.apde_plan_create.restype = ctypes.c_int
     lib.apde_plan_create.argtypes = [ctypes.POINTER(_vp), ctypes.POINTER(PlanDesc)]
     lib.apde_plan_destroy.restype = ctypes.c_int
@@ -140,7 +143,7 @@ EXACT_PATHS = {"auto": 0, "small": 1, "ring": 2}
 
 
 def solve(mode: str, grid: np.ndarray, noise_h, noise_v, source, tol: float, max_iter: int,
-          check_every: int = 0, temporal_depth: int = 0, exact_path: str = "auto"):
+          check_every: int = 0, temporal_depth: int = 0, exact_path: str = "auto", n_gpus: int = 1):
     """One relaxation solve on the GPU.  `grid` (float64, C-order) is updated in place.
 
     mode: "exact" (bit-exact wavefront, fp64), "redblack" (fp64) or "redblack32" (fp32).
@@ -161,6 +164,10 @@ def solve(mode: str, grid: np.ndarray, noise_h, noise_v, source, tol: float, max
     if mode == "exact":
         rc = lib.apde_solve_exact_f64_path(*head, _ptr(hist), ctypes.byref(iters), ctypes.byref(ksec),
                                            EXACT_PATHS[exact_path])
+    elif mode in ("redblack", "redblack64", "redblack32") and n_gpus > 1:
+        rc = lib.apde_solve_redblack_multi(4 if mode == "redblack32" else 8, *head, int(check_every),
+                                           int(temporal_depth), int(n_gpus), _ptr(hist), ctypes.byref(iters),
+                                           ctypes.byref(ksec))
     elif mode in ("redblack", "redblack64"):
         rc = lib.apde_solve_redblack_f64(*head, int(check_every), int(temporal_depth), _ptr(hist),
                                          ctypes.byref(iters), ctypes.byref(ksec))

@@ -16,6 +16,9 @@ variable ``APDE_MODE``; default ``"exact"``:
                     ``APDE_CHECK_EVERY`` (default 32) sweeps.
 * ``redblack32`` -- the same in fp32.
 
+``APDE_GPUS=N`` spreads a red-black solve over N GPUs of the box from this one process (row strips,
+CUDA peer copies); the exact path is sequential along anti-diagonals and always uses one GPU.
+
 ``boundary_fn`` / ``source_fn`` may also be ``numpy`` arrays (extension for large grids where a
 per-node Python callable costs minutes): a boundary array is the initial grid itself (NaN =
 "None", i.e. left at 0.0), a source array holds f(i, j) and is scaled by h**2 like upstream
@@ -134,7 +137,8 @@ def _relax(solver, grid, noise_h, noise_v, source, tol, max_iter, mode):
         mode, grid, noise_h, noise_v, source, tol, max_iter,
         check_every=int(os.environ.get("APDE_CHECK_EVERY", "0")),
         temporal_depth=int(os.environ.get("APDE_TEMPORAL_DEPTH", "0")),
-        exact_path=os.environ.get("APDE_EXACT_PATH", "auto"))
+        exact_path=os.environ.get("APDE_EXACT_PATH", "auto"),
+        n_gpus=int(os.environ.get("APDE_GPUS", "1")))
     solver.residual_history = hist.tolist()
     solver.iterations_run = iters
     solver.kernel_seconds = ksec

@@ -125,6 +125,22 @@ int apde_solve_redblack_f32(double *grid, const double *noise_h, const double *n
                           temporal_depth, residual_history, iterations_run, kernel_seconds);
 }
 
+int apde_solve_redblack_multi(int dtype_bytes, double *grid, const double *noise_h, const double *noise_v,
+                              const double *source, int64_t rows, int64_t cols, double tol,
+                              int64_t max_iter, int check_every, int temporal_depth, int n_gpus,
+                              double *residual_history, int64_t *iterations_run, double *kernel_seconds) {
+    APDE_TRY(check_solve_args("apde_solve_redblack_multi", grid, noise_h, noise_v, rows, cols, max_iter,
+                              residual_history, iterations_run));
+    if (dtype_bytes != 4 && dtype_bytes != 8) {
+        set_error("apde_solve_redblack_multi: dtype_bytes must be 4 or 8");
+        return APDE_EINVAL;
+    }
+    std::lock_guard<std::mutex> lock(g_solve_mutex);
+    return solve_redblack_multi(dtype_bytes, grid, noise_h, noise_v, source, rows, cols, tol, max_iter,
+                                check_every, temporal_depth, n_gpus, residual_history, iterations_run,
+                                kernel_seconds);
+}
+
 int apde_release_cache(void) {
     std::lock_guard<std::mutex> lock(g_solve_mutex);
     release_cached_plan();

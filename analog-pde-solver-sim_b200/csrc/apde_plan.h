@@ -58,6 +58,9 @@ int plan_energy_sums(apde_plan *p, double *sum_h2, double *sum_v2, cudaStream_t 
 int plan_checksum(apde_plan *p, double *sum_out, double *absmax_out, uint64_t *bits_out, cudaStream_t st);
 int plan_ensure_resid(apde_plan *p, int64_t cap);
 void release_cached_plan();
+int solve_redblack_multi(int elem, double *grid, const double *nh, const double *nv, const double *src,
+                         int64_t rows, int64_t cols, double tol, int64_t max_iter, int check_every,
+                         int temporal_depth, int n_gpus, double *hist, int64_t *iters, double *ksec);
 int solve_redblack(int elem, double *grid, const double *nh, const double *nv, const double *src,
                    int64_t rows, int64_t cols, double tol, int64_t max_iter, int check_every,
                    int temporal_depth, double *hist, int64_t *iters, double *ksec);

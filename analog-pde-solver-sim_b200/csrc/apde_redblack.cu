@@ -690,4 +690,151 @@ int solve_redblack(int elem, double *grid, const double *nh, const double *nv, c
     return rc;
 }
 
+// ------------------------------------------------------------------------------------------
+// one-shot host-buffer solve on several GPUs of one box, ONE process (CUDA peer copies over NVLink).
+// Row strips exactly as in the one-process-per-GPU driver (analog_pde_solver/strips.py): per pass of
+// <= temporal_depth sweeps every device relaxes its strip, then pushes its outermost `halo` owned rows
+// into the neighbours' ghost rows (cudaMemcpyPeerAsync on its own stream) and the neighbours' next
+// pass waits for that event.  The ghost rows written belong to the buffer the receiving device's
+// running kernel does not read, so no device ever waits inside a pass.  Same arithmetic per node =>
+// bitwise equal to the single-GPU result.
+// ------------------------------------------------------------------------------------------
+int solve_redblack_multi(int elem, double *grid, const double *nh, const double *nv, const double *src,
+                         int64_t rows, int64_t cols, double tol, int64_t max_iter, int check_every,
+                         int temporal_depth, int n_gpus, double *hist, int64_t *iters, double *ksec) {
+    if (ksec) *ksec = 0.0;
+    if (check_every <= 0) check_every = 32;
+    if (temporal_depth <= 0) temporal_depth = nh ? 2 : 3;
+    int have = 0;
+    if (cudaGetDeviceCount(&have) != cudaSuccess) have = 0;
+    cudaGetLastError();
+    int ndev = std::min(n_gpus, have);
+    const int64_t halo = 2 * (int64_t)temporal_depth;
+    while (ndev > 1 && rows / ndev < std::max<int64_t>(halo, 8)) --ndev;  // strips must be thicker than their halo
+    if (ndev <= 1 || max_iter <= 0 || rows < 3 || cols < 3)
+        return solve_redblack(elem, grid, nh, nv, src, rows, cols, tol, max_iter, check_every, temporal_depth,
+                              hist, iters, ksec);
+    int dev0 = 0;
+    APDE_CUDA(cudaGetDevice(&dev0));
+    struct Strip {
+        apde_plan *plan = nullptr;
+        cudaStream_t st = nullptr;
+        cudaEvent_t halo_sent = nullptr, t0 = nullptr, t1 = nullptr;
+    };
+    std::vector<Strip> sp((size_t)ndev);
+    auto cleanup = [&]() {
+        for (int g = 0; g < ndev; ++g) {
+            cudaSetDevice(g);
+            if (sp[g].halo_sent) cudaEventDestroy(sp[g].halo_sent);
+            if (sp[g].t0) cudaEventDestroy(sp[g].t0);
+            if (sp[g].t1) cudaEventDestroy(sp[g].t1);
+            if (sp[g].st) cudaStreamDestroy(sp[g].st);
+            delete sp[g].plan;
+        }
+        cudaSetDevice(dev0);
+    };
+#define MG_TRY(call)              \
+    do {                          \
+        int rc__ = (call);        \
+        if (rc__ != APDE_OK) {    \
+            cleanup();            \
+            return rc__;          \
+        }                         \
+    } while (0)
+#define MG_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));      \
+            cleanup();                                                                             \
+            return APDE_ECUDA;                                                                     \
+        }                                                                                          \
+    } while (0)
+    for (int g = 0; g < ndev; ++g) {
+        MG_CUDA(cudaSetDevice(g));
+        for (int o = g - 1; o <= g + 1; o += 2) {  // direct NVLink stores where the topology allows
+            int can = 0;
+            if (o >= 0 && o < ndev && cudaDeviceCanAccessPeer(&can, g, o) == cudaSuccess && can) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(o, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                cudaGetLastError();
+            }
+        }
+        apde_plan_desc d{};
+        d.dtype_bytes = elem;
+        d.has_noise = (nh != nullptr);
+        d.has_source = (src != nullptr);
+        d.temporal_depth = temporal_depth;
+        d.grows = rows;
+        d.cols = cols;
+        d.row_begin = rows * g / ndev;
+        d.row_end = rows * (g + 1) / ndev;
+        MG_TRY(plan_create(&sp[g].plan, &d));
+        MG_CUDA(cudaStreamCreateWithFlags(&sp[g].st, cudaStreamNonBlocking));
+        MG_CUDA(cudaEventCreateWithFlags(&sp[g].halo_sent, cudaEventDisableTiming));
+        MG_CUDA(cudaEventCreate(&sp[g].t0));
+        MG_CUDA(cudaEventCreate(&sp[g].t1));
+        MG_TRY(plan_upload(sp[g].plan, grid, nh, nv, src));
+    }
+    int64_t done = 0;
+    bool stop = false;
+    float total_ms = 0.f;
+    std::vector<double> part((size_t)check_every);
+    while (done < max_iter && !stop) {
+        const int64_t n = std::min<int64_t>(check_every, max_iter - done);
+        for (int g = 0; g < ndev; ++g) {
+            MG_CUDA(cudaSetDevice(g));
+            MG_CUDA(cudaEventRecord(sp[g].t0, sp[g].st));
+        }
+        for (int64_t k = 0; k < n; k += temporal_depth) {
+            const int64_t m = std::min<int64_t>(temporal_depth, n - k);
+            for (int g = 0; g < ndev; ++g) {
+                MG_CUDA(cudaSetDevice(g));
+                // the ghost rows this pass reads were written by the neighbours' previous halo pushes
+                if (g > 0) MG_CUDA(cudaStreamWaitEvent(sp[g].st, sp[g - 1].halo_sent, 0));
+                if (g + 1 < ndev) MG_CUDA(cudaStreamWaitEvent(sp[g].st, sp[g + 1].halo_sent, 0));
+                MG_TRY(plan_run(sp[g].plan, m, done + k, 0, sp[g].st));
+            }
+            for (int g = 0; g < ndev; ++g) {
+                MG_CUDA(cudaSetDevice(g));
+                for (int side = 0; side < 2; ++side) {
+                    const int o = side == 0 ? g - 1 : g + 1;
+                    if (o < 0 || o >= ndev) continue;
+                    void *send = nullptr, *recv_unused = nullptr, *osend_unused = nullptr, *orecv = nullptr;
+                    int64_t nb = 0, onb = 0;
+                    MG_TRY(plan_halo(sp[g].plan, side, &send, &recv_unused, &nb));
+                    MG_TRY(plan_halo(sp[o].plan, 1 - side, &osend_unused, &orecv, &onb));
+                    MG_CUDA(cudaMemcpyPeerAsync(orecv, o, send, g, (size_t)nb, sp[g].st));
+                }
+                MG_CUDA(cudaEventRecord(sp[g].halo_sent, sp[g].st));
+            }
+        }
+        std::fill(hist + done, hist + done + n, 0.0);
+        for (int g = 0; g < ndev; ++g) {
+            MG_CUDA(cudaSetDevice(g));
+            MG_CUDA(cudaEventRecord(sp[g].t1, sp[g].st));
+            MG_TRY(plan_read_residuals(sp[g].plan, done, n, part.data(), sp[g].st));
+            for (int64_t k = 0; k < n; ++k)
+                if (part[(size_t)k] > hist[done + k]) hist[done + k] = part[(size_t)k];
+            float ms = 0.f;
+            MG_CUDA(cudaEventElapsedTime(&ms, sp[g].t0, sp[g].t1));
+            if (g == 0) total_ms += ms;
+        }
+        for (int64_t k = 0; k < n; ++k)
+            if (hist[done + k] < tol) stop = true;
+        done += n;
+    }
+    for (int g = 0; g < ndev; ++g) {
+        MG_CUDA(cudaSetDevice(g));
+        MG_CUDA(cudaStreamSynchronize(sp[g].st));
+        MG_TRY(plan_download(sp[g].plan, grid));
+    }
+    *iters = done;
+    if (ksec) *ksec = total_ms * 1e-3;
+    cleanup();
+#undef MG_TRY
+#undef MG_CUDA
+    return APDE_OK;
+}
+
 }  // namespace apde

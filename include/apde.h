@@ -82,6 +82,15 @@ int apde_solve_redblack_f32(double *grid, const double *noise_h, const double *n
                             double *residual_history, int64_t *iterations_run,
                             double *kernel_seconds);
 
+/* The same one-shot solve spread over up to n_gpus devices of this box from ONE process: row strips,
+ * halo rows pushed to the neighbours with CUDA peer copies over NVLink once per fused pass, per-sweep
+ * residuals max-combined on the host.  dtype_bytes 8 = fp64, 4 = fp32.  Result is bitwise equal to
+ * the single-GPU solve.  (The one-process-per-GPU route is apde_plan_* + torch.distributed.) */
+int apde_solve_redblack_multi(int dtype_bytes, double *grid, const double *noise_h, const double *noise_v,
+                              const double *source, int64_t rows, int64_t cols, double tol,
+                              int64_t max_iter, int check_every, int temporal_depth, int n_gpus,
+                              double *residual_history, int64_t *iterations_run, double *kernel_seconds);
+
 /* The red-black one-shot solves keep their device workspace for the next call of the same shape
  * (allocation of several GB costs 10-100 ms); this frees it.  APDE_NO_PLAN_CACHE=1 disables the cache. */
 int apde_release_cache(void);

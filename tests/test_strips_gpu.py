@@ -32,3 +32,26 @@ def test_nccl_strips_bitwise_equal_single_gpu():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "STRIPS_CHECK PASS" in r.stdout
+
+
+@pytest.mark.parametrize("mode,dt", [("redblack", "f64"), ("redblack32", "f32")])
+def test_single_process_multi_gpu_solve_equals_single_gpu(mode, dt):
+    """apde_solve_redblack_multi (one process, CUDA peer copies) == the single-GPU solve bit for bit.
+    With one visible GPU it falls back to the single-GPU path, which keeps the call under test there."""
+    import numpy as np
+    from helpers import random_problem
+    rows, cols = 700, 333
+    g0, nh, nv, s = random_problem(rows, cols, 0.01, seed=44)
+    ref = g0.copy()
+    rh, rn, _ = _backend.solve(mode, ref, nh, nv, s, 0.0, 21, check_every=8, temporal_depth=3)
+    for n in (2, 3, 8):
+        g = g0.copy()
+        h, it, _ = _backend.solve(mode, g, nh, nv, s, 0.0, 21, check_every=8, temporal_depth=3, n_gpus=n)
+        assert it == rn == 21
+        assert g.tobytes() == ref.tobytes(), f"n_gpus={n}"
+        assert h.tobytes() == rh.tobytes(), f"n_gpus={n}"
+    # early stop decision identical too
+    a, b = g0.copy(), g0.copy()
+    ha, na, _ = _backend.solve(mode, a, None, None, s, 1e-4, 4000, check_every=16)
+    hb, nb, _ = _backend.solve(mode, b, None, None, s, 1e-4, 4000, check_every=16, n_gpus=4)
+    assert na == nb and a.tobytes() == b.tobytes() and ha.tobytes() == hb.tobytes()
