@@ -318,7 +318,7 @@ int plan_ensure_resid(apde_plan *p, int64_t cap) {
 // (owned + ghost rows) must lie inside the window.
 template <typename T>
 static int upload_t(apde_plan *p, int64_t win_lo, int64_t win_hi, const double *grid, const double *nh,
-                    const double *nv, const double *src) {
+                    const double *nv, const double *src, bool wait) {
     const Geo g = make_geo(p);
     const int64_t grows = p->d.grows, cols = p->d.cols;
     const int64_t r0 = p->row0, r1 = p->row0 + p->lrows;  // global rows [r0, r1) the strip holds
@@ -358,7 +358,9 @@ static int upload_t(apde_plan *p, int64_t win_lo, int64_t win_hi, const double *
     }
     APDE_CUDA(cudaGetLastError());
     APDE_CUDA(cudaMemcpyAsync(p->u[1].p, p->u[0].p, p->plane_elems() * sizeof(T), cudaMemcpyDeviceToDevice, 0));
-    APDE_CUDA(cudaStreamSynchronize(0));
+    // from pinned host memory the copies above are asynchronous; callers driving several devices
+    // queue all uploads first and wait afterwards (every GPU has its own PCIe link)
+    if (wait) APDE_CUDA(cudaStreamSynchronize(0));
     p->cur = 0;
     p->pass_open = false;
     p->filled = true;
@@ -366,15 +368,20 @@ static int upload_t(apde_plan *p, int64_t win_lo, int64_t win_hi, const double *
     return APDE_OK;
 }
 
-int plan_upload_rows(apde_plan *p, int64_t win_lo, int64_t win_hi, const double *grid, const double *nh,
-                     const double *nv, const double *src) {
+static int plan_upload_rows_impl(apde_plan *p, int64_t win_lo, int64_t win_hi, const double *grid,
+                                 const double *nh, const double *nv, const double *src, bool wait) {
     if (!p || !grid) {
         set_error("plan_upload: NULL argument");
         return APDE_EINVAL;
     }
     APDE_CUDA(cudaSetDevice(p->device));
-    return p->elem == 8 ? upload_t<double>(p, win_lo, win_hi, grid, nh, nv, src)
-                        : upload_t<float>(p, win_lo, win_hi, grid, nh, nv, src);
+    return p->elem == 8 ? upload_t<double>(p, win_lo, win_hi, grid, nh, nv, src, wait)
+                        : upload_t<float>(p, win_lo, win_hi, grid, nh, nv, src, wait);
+}
+
+int plan_upload_rows(apde_plan *p, int64_t win_lo, int64_t win_hi, const double *grid, const double *nh,
+                     const double *nv, const double *src) {
+    return plan_upload_rows_impl(p, win_lo, win_hi, grid, nh, nv, src, true);
 }
 
 int plan_upload(apde_plan *p, const double *grid, const double *nh, const double *nv, const double *src) {
@@ -405,7 +412,11 @@ int plan_fill(apde_plan *p, const apde_fill_desc *f) {
 }
 
 // `out` covers global rows [win_lo, win_hi); the owned rows inside the window are written.
+static int plan_download_rows_impl(apde_plan *p, int64_t win_lo, int64_t win_hi, double *out, bool wait);
 int plan_download_rows(apde_plan *p, int64_t win_lo, int64_t win_hi, double *out) {
+    return plan_download_rows_impl(p, win_lo, win_hi, out, true);
+}
+static int plan_download_rows_impl(apde_plan *p, int64_t win_lo, int64_t win_hi, double *out, bool wait) {
     if (!p || !out || win_lo < 0 || win_hi > p->d.grows || win_lo >= win_hi) {
         set_error("plan_download: bad argument");
         return APDE_EINVAL;
@@ -422,7 +433,8 @@ int plan_download_rows(apde_plan *p, int64_t win_lo, int64_t win_hi, double *out
     else
         unpack_kernel<float><<<p->sm_count * 8, 256>>>(p->U<float>(p->cur), g, stage, lo, hi - lo);
     APDE_CUDA(cudaGetLastError());
-    APDE_CUDA(cudaMemcpy(out + (size_t)(lo - win_lo) * g.cols, stage, nrow * g.cols * 8, cudaMemcpyDeviceToHost));
+    APDE_CUDA(cudaMemcpyAsync(out + (size_t)(lo - win_lo) * g.cols, stage, nrow * g.cols * 8, cudaMemcpyDeviceToHost, 0));
+    if (wait) APDE_CUDA(cudaStreamSynchronize(0));
     p->launches += 1;
     return APDE_OK;
 }
@@ -774,7 +786,11 @@ int solve_redblack_multi(int elem, double *grid, const double *nh, const double 
         MG_CUDA(cudaEventCreateWithFlags(&sp[g].halo_sent, cudaEventDisableTiming));
         MG_CUDA(cudaEventCreate(&sp[g].t0));
         MG_CUDA(cudaEventCreate(&sp[g].t1));
-        MG_TRY(plan_upload(sp[g].plan, grid, nh, nv, src));
+        MG_TRY(plan_upload_rows_impl(sp[g].plan, 0, rows, grid, nh, nv, src, false));  // queued, not waited for
+    }
+    for (int g = 0; g < ndev; ++g) {
+        MG_CUDA(cudaSetDevice(g));
+        MG_CUDA(cudaStreamSynchronize(0));
     }
     int64_t done = 0;
     bool stop = false;
@@ -827,7 +843,11 @@ int solve_redblack_multi(int elem, double *grid, const double *nh, const double 
     for (int g = 0; g < ndev; ++g) {
         MG_CUDA(cudaSetDevice(g));
         MG_CUDA(cudaStreamSynchronize(sp[g].st));
-        MG_TRY(plan_download(sp[g].plan, grid));
+        MG_TRY(plan_download_rows_impl(sp[g].plan, 0, rows, grid, false));  // all devices copy back concurrently
+    }
+    for (int g = 0; g < ndev; ++g) {
+        MG_CUDA(cudaSetDevice(g));
+        MG_CUDA(cudaStreamSynchronize(0));
     }
     *iters = done;
     if (ksec) *ksec = total_ms * 1e-3;
