@@ -356,16 +356,18 @@ __global__ void __launch_bounds__(1024, 1) exact_ring_kernel(K2Params p) {
     for (long long t = c; t < p.n_sweeps; t += G, ++m) {
         const long long mpred = (c == 0) ? m - 1 : m;  // index of sweep t-1 in pred's own sequence
         double mx = 0.0;
-        for (int d = 2; d <= dmax; ++d) {
-            if (t > 0 && tid == 0) {
-                // sweep t-1 must have finished diagonal d+1 (RAW on south/east, WAR on this diagonal)
-                const unsigned long long need =
-                    (unsigned long long)(mpred * ND + (long long)(min(d + 1, dmax) - 1));
-                const unsigned long long *flag = p.progress + (size_t)pred * 16;
-                while (ld_acquire_u64(flag) < need) {
-                }
+        // sweep t-1 must have finished diagonal d+1 before this sweep touches diagonal d (RAW on
+        // south/east, WAR on the diagonal itself).  Thread 0 polls for the NEXT diagonal while the rest
+        // of the block is still finishing the current one, so one barrier per diagonal suffices.
+        auto wait_pred = [&](int d) {
+            const unsigned long long need = (unsigned long long)(mpred * ND + (long long)(min(d + 1, dmax) - 1));
+            const unsigned long long *flag = p.progress + (size_t)pred * 16;
+            while (ld_acquire_u64(flag) < need) {
             }
-            __syncthreads();
+        };
+        if (t > 0 && tid == 0) wait_pred(2);
+        __syncthreads();
+        for (int d = 2; d <= dmax; ++d) {
             const int ilo = max(1, d - (cols - 2)), ihi = min(rows - 2, d - 1);
             const double *up = U + (long long)(d - 1) * P;  // diagonal d-1: north/west, this sweep
             const double *dn = U + (long long)(d + 1) * P;  // diagonal d+1: south/east, previous sweep
@@ -387,6 +389,7 @@ __global__ void __launch_bounds__(1024, 1) exact_ring_kernel(K2Params p) {
                 mx = max_ignore_nan(mx, fabs(__dsub_rn(nw, old)));
                 __stcg(me + i, nw);
             }
+            if (t > 0 && tid == 0 && d < dmax) wait_pred(d + 1);
             __syncthreads();
             if (tid == 0)
                 st_release_u64(p.progress + (size_t)c * 16, (unsigned long long)(m * ND + (d - 1)));
