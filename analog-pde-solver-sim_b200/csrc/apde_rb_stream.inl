@@ -113,6 +113,55 @@ __device__ __forceinline__ void st_vec16(float *p, const float *w) {
                  : "memory");
 }
 
+#ifdef RBS_TMA
+// ---- optional bulk-async (TMA, cp.async.bulk) feed of the u rows: per warp a FIFO ring of row
+// segments in shared memory, filled RBS_TMA_AHEAD rows ahead by one elected lane, completion tracked by
+// one mbarrier per slot.  Keeps many more bytes in flight per SM than the register prefetch can.
+#ifndef RBS_TMA_SLOTS
+#define RBS_TMA_SLOTS 8
+#endif
+#ifndef RBS_TMA_AHEAD
+#define RBS_TMA_AHEAD 6
+#endif
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void lds_vec16(double *w, unsigned addr) {
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(w[0]), "=d"(w[1]) : "r"(addr));
+}
+__device__ __forceinline__ void lds_vec16(float *w, unsigned addr) {
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w[0]), "=f"(w[1]), "=f"(w[2]), "=f"(w[3]) : "r"(addr));
+}
+template <int C>
+__device__ __forceinline__ void lds_row(T (&w)[C], unsigned addr) {
+    constexpr int PER = 16 / (int)sizeof(T);
+#pragma unroll
+    for (int k = 0; k < C / PER; ++k) lds_vec16(&w[k * PER], addr + 16 * k);
+}
+#endif
+
 template <int C>
 __device__ __forceinline__ void load_row(T (&w)[C], const T *p) {
     constexpr int PER = 16 / (int)sizeof(T);
@@ -151,6 +200,21 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
 #pragma unroll
     for (int t = 0; t < TD; ++t) mx[t] = (T)0;
 
+#ifdef RBS_TMA
+    constexpr int TS = RBS_TMA_SLOTS, TA = RBS_TMA_AHEAD;
+    constexpr unsigned ROWB = 32u * C * (unsigned)sizeof(T);  // bytes of one warp row segment
+    static_assert(TA + 1 <= TS, "TMA ring too shallow");
+    extern __shared__ __align__(128) unsigned char rbs_smem[];
+    const unsigned wsm = (unsigned)__cvta_generic_to_shared(rbs_smem) + (unsigned)(threadIdx.x >> 5) * (TS * ROWB + 8 * TS);
+    const unsigned bars = wsm + TS * ROWB;
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < TS; ++k) mbar_init(bars + 8 * k, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    unsigned issued = 0, consumed = 0;  // FIFO counters over the whole kernel (slot = n % TS, parity = (n / TS) & 1)
+#endif
     for (long long item = warp_id; item < a.n_items; item += n_warps) {
         const long long bsel = item / a.n_strips;
         const long long sidx = item - bsel * a.n_strips;
@@ -184,10 +248,41 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
         for (int k = 0; k < NW; ++k)
 #pragma unroll
             for (int q = 0; q < C; ++q) w[k][q] = (T)0;
+#ifdef RBS_TMA
+        // rows rs .. r_load_end are fed in order: issue TA rows ahead of their consumption
+        // exactly the rows the item consumes: RBS_PF in the prologue + one per iteration of the chunked loop
+        // (nothing may still be in flight towards this CTA's shared memory when the item -- or the kernel -- ends)
+        const int r_load_end = rs + RBS_PF + ((r_last - rs) / NW + 1) * NW - 1;
+        const T *pin0 = a.in + (long long)rs * pitch + (a.padl + sidx * VW - HCA);  // lane 0's address of row rs
+        int next_issue = rs;
+        auto tma_issue_upto = [&](int row_limit) {
+            // warp-uniform loop; lane 0 arms the barrier and launches the copy
+            while (next_issue <= row_limit && next_issue <= r_load_end) {
+                if (lane == 0) {
+                    const unsigned slot = issued % TS;
+                    mbar_expect_tx(bars + 8 * slot, ROWB);
+                    tma_load_1d(wsm + slot * ROWB, pin0 + (long long)(next_issue - rs) * pitch, ROWB, bars + 8 * slot);
+                }
+                ++issued;
+                ++next_issue;
+            }
+        };
+        auto tma_consume = [&](T (&dst)[C]) {
+            const unsigned slot = consumed % TS, par = (consumed / TS) & 1u;
+            mbar_wait(bars + 8 * slot, par);
+            lds_row<C>(dst, wsm + slot * ROWB + (unsigned)lane * (C * (unsigned)sizeof(T)));
+            ++consumed;
+        };
+        __syncwarp();
+        tma_issue_upto(rs + RBS_PF - 1 + TA);
+#pragma unroll
+        for (int k = 0; k < RBS_PF; ++k) tma_consume(w[k]);
+#else
 #pragma unroll
         for (int k = 0; k < RBS_PF; ++k) {
             load_row<C>(w[k], pin + k * pitch);  // rows past either end are zero padding
         }
+#endif
         unsigned act = 0, cnt = 0;  // bit s: the row stage s handles this iteration is relaxed / counted
         T mxl[TD];
 #pragma unroll
@@ -199,7 +294,13 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
                 const int r = rc + rr;
                 // unconditional (padding rows make every address valid): the load lands straight in
                 // its window slot and nothing waits on it until the row is first used
+#ifdef RBS_TMA
+                __syncwarp();  // every lane is done with the slot that is about to be refilled
+                tma_issue_upto(r + RBS_PF + TA);
+                tma_consume(w[(rr + RBS_PF) % NW]);
+#else
                 load_row<C>(w[(rr + RBS_PF) % NW], pin + RBS_PF * pitch);
+#endif
                 act = (act << 1) | (((unsigned)(r - 2 - ra) < upd_span) ? 1u : 0u);
                 cnt = (cnt << 1) | (((unsigned)(r - 1 - rb0) < own_span) ? 1u : 0u);
                 // column parity relaxed by stage s in this iteration: (rr + 1 + (LAG-1)*s) & 1
@@ -209,7 +310,9 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
                 if (L2PF > 0 && r + L2PF <= re) {  // not past the item's last row (another warp's block)
                     // two-level software prefetch: HBM -> L2 far ahead (hides DRAM latency at low
                     // occupancy), L2 -> L1 / registers a few rows ahead
+#ifndef RBS_TMA
                     prefetch_l2(pin + (long long)L2PF * pitch);
+#endif
                     if (SRC) prefetch_l2(psrc + (long long)L2PF * pitch);
                     if (NOISE) {
                         prefetch_l2(pgh + (long long)L2PF * pitch);
@@ -315,10 +418,17 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
 
 template <int C, int TD, bool NOISE, bool SRC>
 int launch_pass(apde_plan *p, const StreamArgs &a, cudaStream_t st) {
+#ifdef RBS_TMA
+    constexpr size_t smem = (size_t)(RBS_THREADS / 32) * (RBS_TMA_SLOTS * 32 * C * sizeof(T) + 8 * RBS_TMA_SLOTS);
+#else
+    constexpr size_t smem = 0;
+#endif
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
         int n = 0;
-        APDE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, rb_stream_kernel<C, TD, NOISE, SRC>, RBS_THREADS, 0));
+        if (smem > 48 * 1024)
+            APDE_CUDA(cudaFuncSetAttribute(rb_stream_kernel<C, TD, NOISE, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        APDE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, rb_stream_kernel<C, TD, NOISE, SRC>, RBS_THREADS, smem));
         blocks_per_sm = n > 0 ? n : 1;
     }
     const long long warps_per_block = RBS_THREADS / 32;
@@ -326,7 +436,7 @@ int launch_pass(apde_plan *p, const StreamArgs &a, cudaStream_t st) {
     const long long need = (a.n_items + warps_per_block - 1) / warps_per_block;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    rb_stream_kernel<C, TD, NOISE, SRC><<<(unsigned)grid, RBS_THREADS, 0, st>>>(a);
+    rb_stream_kernel<C, TD, NOISE, SRC><<<(unsigned)grid, RBS_THREADS, smem, st>>>(a);
     p->launches++;
     return APDE_OK;
 }
