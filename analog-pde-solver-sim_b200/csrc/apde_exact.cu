@@ -341,8 +341,16 @@ struct K2Params {
     long long n_sweeps;             // sweeps in this launch
 };
 
-template <bool HAS_NOISE, bool HAS_SRC>
-__global__ void __launch_bounds__(1024, 1) exact_ring_kernel(K2Params p) {
+#ifndef K2_SMALL_THREADS
+#define K2_SMALL_THREADS 512  // CTA size of the two-CTAs-per-SM configuration
+#endif
+#ifndef K2_SMALL_MINBLOCKS
+#define K2_SMALL_MINBLOCKS 2
+#endif
+// MAXT / MINB only shape the register budget (__launch_bounds__): <1024,1> and <512,2> get 64 registers,
+// <384,2> 85, <256,2> 128.
+template <bool HAS_NOISE, bool HAS_SRC, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) exact_ring_kernel(K2Params p) {
     const int rows = p.rows, cols = p.cols;
     const long long P = p.P;
     const int G = gridDim.x, c = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
@@ -637,7 +645,8 @@ struct RingCfg {
 template <bool N, bool S>
 static const void *ring_fn(int npt) {
     switch (npt) {
-        case 0: return (const void *)exact_ring_kernel<N, S>;
+        case 0: return (const void *)exact_ring_kernel<N, S, 1024, 1>;
+        case -1: return (const void *)exact_ring_kernel<N, S, K2_SMALL_THREADS, K2_SMALL_MINBLOCKS>;
         case 1: return (const void *)exact_ring2_kernel<N, S, 1>;
         case 2: return (const void *)exact_ring2_kernel<N, S, 2>;
         case 4: return (const void *)exact_ring2_kernel<N, S, 4>;
@@ -656,7 +665,7 @@ static int ring_dispatch(bool noise, bool src, const K2Params &p, const RingCfg 
     int kb = cfg.kb;
     void *args2[] = {(void *)&p, (void *)&kb};
     void *args1[] = {(void *)&p};
-    APDE_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(cfg.block), cfg.npt ? args2 : args1, cfg.smem, st));
+    APDE_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(cfg.block), cfg.npt > 0 ? args2 : args1, cfg.smem, st));
     return APDE_OK;
 }
 
@@ -687,9 +696,10 @@ static int ring_configure(bool noise, bool src, int64_t rows, int64_t cols, int6
         cfg->smem = smem2;
         if (const char *v = getenv("APDE_RING_BATCH")) cfg->kb = std::max(1, atoi(v));
     } else {
-        cfg->block = maxdiag > 2048 ? (many ? 512 : 1024) : (maxdiag > 512 ? 512 : 256);
+        cfg->block = maxdiag > 2048 ? (many ? K2_SMALL_THREADS : 1024) : (maxdiag > 512 ? 512 : 256);
         if (const char *v = getenv("APDE_RING_BLOCK")) cfg->block = std::min(1024, std::max(64, atoi(v) / 32 * 32));
-        cfg->npt = 0;
+        // npt 0: kernel compiled for 1024-thread CTAs; -1: for K2_SMALL_THREADS-thread CTAs (more registers)
+        cfg->npt = cfg->block <= K2_SMALL_THREADS ? -1 : 0;
         cfg->smem = 0;
     }
     const void *fn = ring_fn(noise, src, cfg->npt);
