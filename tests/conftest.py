@@ -12,6 +12,17 @@ for p in (PKG_DIR, ROOT, os.path.dirname(os.path.abspath(__file__))):
         sys.path.insert(0, p)
 
 
+def _ensure_built():
+    """Build libapde.so / the oracle on first use (nvcc cross-compiles without a GPU)."""
+    lib = os.path.join(PKG_DIR, "lib", "libapde.so")
+    if not os.path.exists(lib) or not os.path.exists(os.path.join(ROOT, "oracle", "libapde_oracle.so")):
+        import __graft_entry__
+        __graft_entry__.build()
+
+
+_ensure_built()
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
 
