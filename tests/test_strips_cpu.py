@@ -109,7 +109,7 @@ def _free_port():
 @pytest.mark.parametrize("world,rows,cols,depth,n_sweeps,overlap", [
     (2, 40, 22, 2, 7, False), (2, 41, 19, 3, 6, True), (3, 60, 17, 2, 5, True)])
 def test_strips_equal_single_strip_bitwise(world, rows, cols, depth, n_sweeps, overlap):
-    mgr = mp.Manager()
+    mgr = mp.get_context("spawn").Manager()  # never fork a process that already runs OpenMP threads
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), rows, cols, depth, n_sweeps, overlap, out), nprocs=world, join=True)
     assert len(out) == world
