@@ -189,8 +189,9 @@ class AnalogPDESolver:
         rows, cols = self.rows, self.cols
         grid = _initial_grid(rows, cols, boundary_fn)
         source = _source_term(rows, cols, source_fn)
-        # all-ones links divide exactly (x / 1.0 == x): skip them, the result has the same bits
-        ideal = not (self.noise_level > 0)
+        # all-ones links divide exactly (x / 1.0 == x): skip them, the result has the same bits.  The
+        # arrays are checked, not the flag, so links edited after construction are honoured like upstream.
+        ideal = (not (self.noise_level > 0)) and bool((self._noise_h == 1.0).all() and (self._noise_v == 1.0).all())
         return _relax(self, grid, None if ideal else self._noise_h, None if ideal else self._noise_v,
                       source, tol, max_iter, _resolve_mode(mode, self.backend_mode))
 
