@@ -38,8 +38,6 @@ struct apde_plan {
     template <typename T> T *S() const { return src.p ? src.as<T>() + rowpad * pitch : nullptr; }
     template <typename T> T *GH() const { return gh.p ? gh.as<T>() + rowpad * pitch : nullptr; }
     template <typename T> T *GV() const { return gv.p ? gv.as<T>() + rowpad * pitch : nullptr; }
-    // element offset of (local row li, column j)
-    size_t off(int64_t li, int64_t j) const { return (size_t)li * (size_t)pitch + (size_t)(padl + j); }
 };
 
 namespace apde {

@@ -217,12 +217,6 @@ __global__ void energy_kernel(const T *__restrict__ u, Geo g, double *out /*[0]=
     }
 }
 
-template <typename T>
-__global__ void resid_to_f64_kernel(const T *in, double *out, long long n) {
-    const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (k < n) out[k] = (double)in[k];
-}
-
 // ------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------
