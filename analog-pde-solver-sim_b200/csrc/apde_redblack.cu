@@ -621,6 +621,7 @@ int solve_redblack(int elem, double *grid, const double *nh, const double *nv, c
     }
     if (check_every <= 0) check_every = 32;
     if (temporal_depth <= 0) temporal_depth = nh ? 2 : 3;  // measured best fused depth per variant
+    temporal_depth = std::min(temporal_depth, 4);
     if (rows < 3 || cols < 3) {
         const int64_t n = (0.0 < tol) ? std::min<int64_t>(check_every, max_iter) : max_iter;
         for (int64_t k = 0; k < n; ++k) hist[k] = 0.0;
@@ -711,6 +712,7 @@ int solve_redblack_multi(int elem, double *grid, const double *nh, const double 
     if (ksec) *ksec = 0.0;
     if (check_every <= 0) check_every = 32;
     if (temporal_depth <= 0) temporal_depth = nh ? 2 : 3;
+    temporal_depth = std::min(temporal_depth, 4);
     int have = 0;
     if (cudaGetDeviceCount(&have) != cudaSuccess) have = 0;
     cudaGetLastError();
