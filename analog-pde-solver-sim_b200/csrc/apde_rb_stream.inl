@@ -166,6 +166,27 @@ __device__ __forceinline__ void lds_row(T (&w)[C], unsigned addr) {
 }
 #endif
 
+// Operand load that stays where it is written: a volatile asm is not sunk towards its first use, so
+// an iteration's operand loads really are in flight before the arithmetic starts.
+__device__ __forceinline__ double ld_operand(const double *p) {
+#ifdef RBS_PINNED_OPERAND_LOADS
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+__device__ __forceinline__ float ld_operand(const float *p) {
+#ifdef RBS_PINNED_OPERAND_LOADS
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+
 template <int C>
 __device__ __forceinline__ void load_row(T (&w)[C], const T *p) {
     constexpr int PER = 16 / (int)sizeof(T);
@@ -340,12 +361,12 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
 #pragma unroll
                     for (int q = p; q < C; q += 2) {
                         // unconditional: rows of inactive stages are padding or real rows, both readable
-                        if (SRC) o_sv[s][q >> 1] = __ldg(psrc + ro + q);
+                        if (SRC) o_sv[s][q >> 1] = ld_operand(psrc + ro + q);
                         if (NOISE) {
-                            o_gn[s][q >> 1] = __ldg(pgv + ro - pitch + q);
-                            o_gs[s][q >> 1] = __ldg(pgv + ro + q);
-                            o_gw[s][q >> 1] = __ldg(pgh + ro + q - 1);
-                            o_ge[s][q >> 1] = __ldg(pgh + ro + q);
+                            o_gn[s][q >> 1] = ld_operand(pgv + ro - pitch + q);
+                            o_gs[s][q >> 1] = ld_operand(pgv + ro + q);
+                            o_gw[s][q >> 1] = ld_operand(pgh + ro + q - 1);
+                            o_ge[s][q >> 1] = ld_operand(pgh + ro + q);
                         }
                     }
                 };
