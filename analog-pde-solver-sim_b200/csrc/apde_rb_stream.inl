@@ -78,7 +78,9 @@ constexpr int L2PF_ROWS = RBS_L2PF;  // rows ahead that are pulled from HBM into
 // the fp32 source-only kernels gain from 12 warps/SM (168 registers, no spills); every other variant
 // loses more to spills than it gains from occupancy.
 constexpr int rbs_min_blocks(int elem_bytes, int lane_cols, bool noise) {
-#ifdef RBS_F32_MINBLOCKS
+#ifdef RBS_MINBLOCKS_ALL
+    return RBS_MINBLOCKS_ALL;
+#elif defined(RBS_F32_MINBLOCKS)
     return (elem_bytes == 4 && lane_cols == 4 && !noise) ? RBS_F32_MINBLOCKS : 1;
 #else
     return (elem_bytes == 4 && lane_cols == 4 && !noise) ? 3 : 1;
