@@ -29,7 +29,7 @@ EXPORTED_SYMBOLS = (
     "apde_solve_exact_f64", "apde_solve_exact_f64_path", "apde_solve_redblack_f64", "apde_solve_redblack_f32", "apde_solve_redblack_multi", "apde_release_cache",
     "apde_plan_create", "apde_plan_destroy", "apde_plan_upload", "apde_plan_upload_rows", "apde_plan_download_rows", "apde_plan_fill",
     "apde_plan_download", "apde_plan_clear_residuals", "apde_plan_run", "apde_plan_halo", "apde_plan_residuals",
-    "apde_plan_read_residuals", "apde_plan_launch_count", "apde_plan_checksum", "apde_plan_checksum_bits", "apde_memcpy_dtod", "apde_selftest_division", "apde_plan_energy_sums",
+    "apde_plan_read_residuals", "apde_plan_launch_count", "apde_plan_checksum", "apde_plan_checksum_bits", "apde_memcpy_dtod", "apde_selftest_division", "apde_plan_energy_sums", "apde_plan_download_array", "apde_default_temporal_depth",
 )
 
 
@@ -90,6 +90,10 @@ def load():
     lib.apde_plan_upload_rows.argtypes = [_vp, _i64, _i64, _dp, _dp, _dp, _dp]
     lib.apde_plan_download_rows.restype = ctypes.c_int
     lib.apde_plan_download_rows.argtypes = [_vp, _i64, _i64, _dp]
+    lib.apde_default_temporal_depth.restype = ctypes.c_int
+    lib.apde_default_temporal_depth.argtypes = [ctypes.c_int, ctypes.c_int]
+    lib.apde_plan_download_array.restype = ctypes.c_int
+    lib.apde_plan_download_array.argtypes = [_vp, ctypes.c_int, _i64, _i64, _dp]
     lib.apde_plan_fill.restype = ctypes.c_int
     lib.apde_plan_fill.argtypes = [_vp, ctypes.POINTER(FillDesc)]
     lib.apde_plan_download.restype = ctypes.c_int
@@ -120,6 +124,11 @@ def load():
     return lib
 
 
+def default_temporal_depth(dtype: str, has_noise: bool) -> int:
+    """Fused sweeps per HBM pass the library picks for this variant ("f64" / "f32")."""
+    return int(load().apde_default_temporal_depth(8 if dtype in ("f64", "float64") else 4, int(bool(has_noise))))
+
+
 def check(rc: int) -> None:
     if rc != APDE_OK:
         msg = load().apde_last_error()
@@ -140,10 +149,42 @@ def _as_f64(a, shape, name):
 
 
 EXACT_PATHS = {"auto": 0, "small": 1, "ring": 2}
+MODES = ("exact", "redblack", "redblack64", "redblack32")
+
+# Sweeps per C call.  The reference accepts any max_iter because its residual list grows lazily
+# (solver.py:262, :281); here the history buffer of one call is max_iter doubles on the host and on the
+# device, so a "practically unlimited" max_iter is served in chunks that continue from the grid the
+# previous chunk left (Gauss-Seidel's only state), which is bit-identical to one long call.
+MAX_SWEEPS_PER_CALL = 1 << 20
+
+
+def _solve_once(lib, mode, grid, nh, nv, src, tol, max_iter, check_every, temporal_depth, exact_path, n_gpus):
+    rows, cols = grid.shape
+    hist = np.zeros(max(max_iter, 1), dtype=np.float64)
+    iters = ctypes.c_int64(0)
+    ksec = ctypes.c_double(0.0)
+    head = (_ptr(grid), _ptr(nh), _ptr(nv), _ptr(src), rows, cols, float(tol), max_iter)
+    if mode == "exact":
+        rc = lib.apde_solve_exact_f64_path(*head, _ptr(hist), ctypes.byref(iters), ctypes.byref(ksec),
+                                           EXACT_PATHS[exact_path])
+    elif n_gpus > 1:
+        rc = lib.apde_solve_redblack_multi(4 if mode == "redblack32" else 8, *head, int(check_every),
+                                           int(temporal_depth), int(n_gpus), _ptr(hist), ctypes.byref(iters),
+                                           ctypes.byref(ksec))
+    elif mode in ("redblack", "redblack64"):
+        rc = lib.apde_solve_redblack_f64(*head, int(check_every), int(temporal_depth), _ptr(hist),
+                                         ctypes.byref(iters), ctypes.byref(ksec))
+    else:
+        rc = lib.apde_solve_redblack_f32(*head, int(check_every), int(temporal_depth), _ptr(hist),
+                                         ctypes.byref(iters), ctypes.byref(ksec))
+    check(rc)
+    n = int(iters.value)
+    return hist[:max(n, 0)], n, float(ksec.value)
 
 
 def solve(mode: str, grid: np.ndarray, noise_h, noise_v, source, tol: float, max_iter: int,
-          check_every: int = 0, temporal_depth: int = 0, exact_path: str = "auto", n_gpus: int = 1):
+          check_every: int = 0, temporal_depth: int = 0, exact_path: str = "auto", n_gpus: int = 1,
+          omega: Optional[float] = None):
     """One relaxation solve on the GPU.  `grid` (float64, C-order) is updated in place.
 
     mode: "exact" (bit-exact wavefront, fp64), "redblack" (fp64) or "redblack32" (fp32).
@@ -152,33 +193,32 @@ def solve(mode: str, grid: np.ndarray, noise_h, noise_v, source, tol: float, max
     lib = load()
     if grid.dtype != np.float64 or not grid.flags.c_contiguous or grid.ndim != 2:
         raise ValueError("grid must be a C-contiguous float64 2-D array")
+    if mode not in MODES:
+        raise ValueError(f"unknown APDE mode {mode!r} (expected one of {', '.join(MODES)})")
+    if exact_path not in EXACT_PATHS:
+        raise ValueError(f"unknown exact path {exact_path!r} (expected one of {', '.join(EXACT_PATHS)})")
     rows, cols = grid.shape
     nh = _as_f64(noise_h, (rows, cols - 1), "noise_h")
     nv = _as_f64(noise_v, (rows - 1, cols), "noise_v")
     src = _as_f64(source, (rows, cols), "source")
     max_iter = int(max_iter)
-    hist = np.zeros(max(max_iter, 1), dtype=np.float64)
-    iters = ctypes.c_int64(0)
-    ksec = ctypes.c_double(0.0)
-    head = (_ptr(grid), _ptr(nh), _ptr(nv), _ptr(src), rows, cols, float(tol), max_iter)
-    if mode == "exact":
-        rc = lib.apde_solve_exact_f64_path(*head, _ptr(hist), ctypes.byref(iters), ctypes.byref(ksec),
-                                           EXACT_PATHS[exact_path])
-    elif mode in ("redblack", "redblack64", "redblack32") and n_gpus > 1:
-        rc = lib.apde_solve_redblack_multi(4 if mode == "redblack32" else 8, *head, int(check_every),
-                                           int(temporal_depth), int(n_gpus), _ptr(hist), ctypes.byref(iters),
-                                           ctypes.byref(ksec))
-    elif mode in ("redblack", "redblack64"):
-        rc = lib.apde_solve_redblack_f64(*head, int(check_every), int(temporal_depth), _ptr(hist),
-                                         ctypes.byref(iters), ctypes.byref(ksec))
-    elif mode == "redblack32":
-        rc = lib.apde_solve_redblack_f32(*head, int(check_every), int(temporal_depth), _ptr(hist),
-                                         ctypes.byref(iters), ctypes.byref(ksec))
-    else:
-        raise ValueError(f"unknown APDE mode {mode!r} (exact | redblack | redblack32)")
-    check(rc)
-    n = int(iters.value)
-    return hist[:max(n, 0)].copy(), n, float(ksec.value)
+    if max_iter <= MAX_SWEEPS_PER_CALL:
+        hist, n, ksec = _solve_once(lib, mode, grid, nh, nv, src, tol, max_iter, check_every, temporal_depth,
+                                    exact_path, n_gpus)
+        return hist.copy(), n, ksec
+    parts, done, ksec_total = [], 0, 0.0
+    while done < max_iter:
+        chunk = min(MAX_SWEEPS_PER_CALL, max_iter - done)
+        hist, n, ksec = _solve_once(lib, mode, grid, nh, nv, src, tol, chunk, check_every, temporal_depth,
+                                    exact_path, n_gpus)
+        parts.append(hist.copy())
+        done += n
+        ksec_total += ksec
+        # the chunk stopped early, or the stopping sweep sits in its last check interval (solver.py:283-285)
+        tail = 1 if mode == "exact" else (int(check_every) if check_every > 0 else 32)
+        if n < chunk or (n > 0 and bool((hist[max(n - tail, 0):n] < tol).any())):
+            break
+    return (np.concatenate(parts) if parts else np.zeros(0)), done, ksec_total
 
 
 class Plan:
@@ -226,6 +266,15 @@ class Plan:
         if out is None:
             out = np.zeros((g, c), dtype=np.float64)
         check(self._lib.apde_plan_download(self._h, _ptr(out)))
+        return out
+
+    ARRAYS = {"grid": 0, "source": 1, "gh": 2, "gv": 3}
+
+    def download_array(self, which: str, row_lo: int = 0, row_hi: Optional[int] = None) -> np.ndarray:
+        """Rows [row_lo, row_hi) of one of the plan's arrays as float64 (owned rows only; others stay 0)."""
+        row_hi = self.desc.grows if row_hi is None else row_hi
+        out = np.zeros((row_hi - row_lo, self.desc.cols), dtype=np.float64)
+        check(self._lib.apde_plan_download_array(self._h, self.ARRAYS[which], int(row_lo), int(row_hi), _ptr(out)))
         return out
 
     def run(self, n_sweeps: int, sweep_base: int = 0, phase: int = 0, stream: int = 0):

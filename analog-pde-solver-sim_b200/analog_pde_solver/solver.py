@@ -109,10 +109,14 @@ def _initial_grid(rows: int, cols: int, boundary: Union[BoundaryFn, np.ndarray])
 
 
 def _source_term(rows: int, cols: int, source: Union[None, SourceFn, np.ndarray]) -> Optional[np.ndarray]:
-    """h^2 * f with h = 1/(max(rows, cols) - 1); None for the Laplace equation."""
+    """h^2 * f with h = 1/(max(rows, cols) - 1); None for the Laplace equation.
+
+    ``h`` is evaluated first, as upstream does (solver.py:254, :329): a 1 x 1 grid raises
+    ZeroDivisionError there even without a source, so it does here.
+    """
+    h = 1.0 / (max(rows, cols) - 1)
     if source is None:
         return None
-    h = 1.0 / (max(rows, cols) - 1)
     if isinstance(source, np.ndarray):
         if source.shape != (rows, cols):
             raise ValueError(f"source array must have shape {(rows, cols)}, got {source.shape}")
@@ -127,18 +131,48 @@ def _source_term(rows: int, cols: int, source: Union[None, SourceFn, np.ndarray]
 
 
 def _resolve_mode(explicit: Optional[str], instance_default: Optional[str]) -> str:
-    mode = explicit or instance_default or os.environ.get("APDE_MODE") or "exact"
-    return mode.lower()
+    mode = (explicit or instance_default or os.environ.get("APDE_MODE") or "exact").lower()
+    if mode not in _backend.MODES:
+        raise ValueError(f"unknown APDE mode {mode!r}: expected one of {sorted(_backend.MODES)}")
+    return mode
 
 
-def _relax(solver, grid, noise_h, noise_v, source, tol, max_iter, mode):
+def _env_int(name: str, default: int, lo: int) -> int:
+    """Integer option from the environment with a message that names the variable."""
+    raw = os.environ.get(name)
+    if raw is None or raw.strip() == "":
+        return default
+    try:
+        value = int(raw)
+    except ValueError:
+        raise ValueError(f"{name}={raw!r} is not an integer") from None
+    if value < lo:
+        raise ValueError(f"{name}={value} must be >= {lo}")
+    return value
+
+
+def _env_float(name: str, default: Optional[float]) -> Optional[float]:
+    raw = os.environ.get(name)
+    if raw is None or raw.strip() == "":
+        return default
+    try:
+        return float(raw)
+    except ValueError:
+        raise ValueError(f"{name}={raw!r} is not a number") from None
+
+
+def _relax(solver, grid, noise_h, noise_v, source, tol, max_iter, mode, omega=None):
     """The one device call that replaces the reference's sweep loop."""
+    exact_path = os.environ.get("APDE_EXACT_PATH", "auto").lower()
+    if exact_path not in _backend.EXACT_PATHS:
+        raise ValueError(f"APDE_EXACT_PATH={exact_path!r}: expected one of {sorted(_backend.EXACT_PATHS)}")
     hist, iters, ksec = _backend.solve(
         mode, grid, noise_h, noise_v, source, tol, max_iter,
-        check_every=int(os.environ.get("APDE_CHECK_EVERY", "0")),
-        temporal_depth=int(os.environ.get("APDE_TEMPORAL_DEPTH", "0")),
-        exact_path=os.environ.get("APDE_EXACT_PATH", "auto"),
-        n_gpus=int(os.environ.get("APDE_GPUS", "1")))
+        check_every=_env_int("APDE_CHECK_EVERY", 0, 0),
+        temporal_depth=_env_int("APDE_TEMPORAL_DEPTH", 0, 0),
+        exact_path=exact_path,
+        n_gpus=_env_int("APDE_GPUS", 1, 1),
+        omega=omega if omega is not None else _env_float("APDE_OMEGA", None))
     solver.residual_history = hist.tolist()
     solver.iterations_run = iters
     solver.kernel_seconds = ksec

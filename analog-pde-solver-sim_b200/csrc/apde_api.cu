@@ -141,6 +141,10 @@ int apde_solve_redblack_multi(int dtype_bytes, double *grid, const double *noise
                                 kernel_seconds);
 }
 
+int apde_default_temporal_depth(int dtype_bytes, int has_noise) {
+    return default_temporal_depth(dtype_bytes, has_noise != 0);
+}
+
 int apde_release_cache(void) {
     std::lock_guard<std::mutex> lock(g_solve_mutex);
     release_cached_plan();
@@ -167,6 +171,9 @@ int apde_plan_upload_rows(apde_plan *plan, int64_t row_lo, int64_t row_hi, const
 }
 int apde_plan_download_rows(apde_plan *plan, int64_t row_lo, int64_t row_hi, double *out) {
     return plan_download_rows(plan, row_lo, row_hi, out);
+}
+int apde_plan_download_array(apde_plan *plan, int which, int64_t row_lo, int64_t row_hi, double *out) {
+    return plan_download_array(plan, which, row_lo, row_hi, out);
 }
 int apde_plan_fill(apde_plan *plan, const apde_fill_desc *fill) { return plan_fill(plan, fill); }
 int apde_plan_download(apde_plan *plan, double *grid) { return plan_download(plan, grid); }

@@ -48,6 +48,7 @@ int plan_fill(apde_plan *p, const apde_fill_desc *f);
 int plan_download(apde_plan *p, double *grid);
 int plan_upload_rows(apde_plan *p, int64_t win_lo, int64_t win_hi, const double *grid, const double *nh, const double *nv, const double *src);
 int plan_download_rows(apde_plan *p, int64_t win_lo, int64_t win_hi, double *out);
+int plan_download_array(apde_plan *p, int which, int64_t win_lo, int64_t win_hi, double *out);
 int plan_run(apde_plan *p, int64_t n_sweeps, int64_t sweep_base, int phase, cudaStream_t st);
 int plan_clear_residuals(apde_plan *p, int64_t first, int64_t count, cudaStream_t st);
 int plan_halo(apde_plan *p, int side, void **send_ptr, void **recv_ptr, int64_t *nbytes);
@@ -56,6 +57,7 @@ int plan_energy_sums(apde_plan *p, double *sum_h2, double *sum_v2, cudaStream_t 
 int plan_checksum(apde_plan *p, double *sum_out, double *absmax_out, uint64_t *bits_out, cudaStream_t st);
 int plan_ensure_resid(apde_plan *p, int64_t cap);
 void release_cached_plan();
+int default_temporal_depth(int elem, bool noise);
 int solve_redblack_multi(int elem, double *grid, const double *nh, const double *nv, const double *src,
                          int64_t rows, int64_t cols, double tol, int64_t max_iter, int check_every,
                          int temporal_depth, int n_gpus, double *hist, int64_t *iters, double *ksec);

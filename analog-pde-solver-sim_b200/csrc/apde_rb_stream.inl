@@ -532,9 +532,13 @@ int RBS_FN(apde_plan *p, int64_t n_sweeps, int64_t sweep_base, int phase, cudaSt
         const int HCA = ((2 * td + lane_cols - 1) / lane_cols) * lane_cols;
         const int VW = 32 * lane_cols - 2 * HCA;
         a.n_strips = (g.cols + VW - 1) / VW;
-        // edge blocks: first / last row block when that side has a neighbour strip
+        // edge blocks: the leading / trailing row blocks that together hold the `halo` outermost owned
+        // rows on a side with a neighbour strip (those rows are what the halo exchange ships right after
+        // phase 1).  Blocks are rbh >= halo rows, except the last one, which holds the remainder: when
+        // that is shorter than the halo the block before it is an edge block too.
         const bool top_nb = p->ghost_top > 0, bot_nb = p->ghost_bot > 0;
-        long long ea = (top_nb ? 1 : 0), eb = (bot_nb ? 1 : 0);
+        const long long last_rows = owned - (nblk - 1) * a.rbh;
+        long long ea = (top_nb ? 1 : 0), eb = (bot_nb ? (last_rows < p->halo ? 2 : 1) : 0);
         if (ea + eb > nblk) { ea = std::min<long long>(ea, nblk); eb = nblk - ea; }
         if (phase == 0) {
             a.blk_a0 = 0; a.blk_an = nblk; a.blk_b0 = 0; a.blk_bn = 0;

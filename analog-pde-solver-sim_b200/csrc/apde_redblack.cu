@@ -406,14 +406,22 @@ int plan_fill(apde_plan *p, const apde_fill_desc *f) {
 }
 
 // `out` covers global rows [win_lo, win_hi); the owned rows inside the window are written.
-static int plan_download_rows_impl(apde_plan *p, int64_t win_lo, int64_t win_hi, double *out, bool wait);
+// which: 0 = current grid, 1 = source, 2 = gh (conductance of link (i,j)-(i,j+1)), 3 = gv ((i,j)-(i+1,j)).
+static int plan_download_rows_impl(apde_plan *p, int which, int64_t win_lo, int64_t win_hi, double *out, bool wait);
 int plan_download_rows(apde_plan *p, int64_t win_lo, int64_t win_hi, double *out) {
-    return plan_download_rows_impl(p, win_lo, win_hi, out, true);
+    return plan_download_rows_impl(p, 0, win_lo, win_hi, out, true);
 }
-static int plan_download_rows_impl(apde_plan *p, int64_t win_lo, int64_t win_hi, double *out, bool wait) {
-    if (!p || !out || win_lo < 0 || win_hi > p->d.grows || win_lo >= win_hi) {
+int plan_download_array(apde_plan *p, int which, int64_t win_lo, int64_t win_hi, double *out) {
+    return plan_download_rows_impl(p, which, win_lo, win_hi, out, true);
+}
+static int plan_download_rows_impl(apde_plan *p, int which, int64_t win_lo, int64_t win_hi, double *out, bool wait) {
+    if (!p || !out || win_lo < 0 || win_hi > p->d.grows || win_lo >= win_hi || which < 0 || which > 3) {
         set_error("plan_download: bad argument");
         return APDE_EINVAL;
+    }
+    if ((which == 1 && !p->d.has_source) || (which >= 2 && !p->d.has_noise)) {
+        set_error("plan_download: the plan holds no %s array", which == 1 ? "source" : "conductance");
+        return APDE_ESTATE;
     }
     APDE_CUDA(cudaSetDevice(p->device));
     const Geo g = make_geo(p);
@@ -422,10 +430,14 @@ static int plan_download_rows_impl(apde_plan *p, int64_t win_lo, int64_t win_hi,
     const size_t nrow = (size_t)(hi - lo);
     if (p->stage.bytes < nrow * g.cols * 8) APDE_TRY(p->stage.alloc(nrow * g.cols * 8));
     double *stage = p->stage.as<double>();
+    auto pick = [&](auto tag) {
+        using E = decltype(tag);
+        return which == 0 ? p->U<E>(p->cur) : which == 1 ? p->S<E>() : which == 2 ? p->GH<E>() : p->GV<E>();
+    };
     if (p->elem == 8)
-        unpack_kernel<double><<<p->sm_count * 8, 256>>>(p->U<double>(p->cur), g, stage, lo, hi - lo);
+        unpack_kernel<double><<<p->sm_count * 8, 256>>>(pick(double{}), g, stage, lo, hi - lo);
     else
-        unpack_kernel<float><<<p->sm_count * 8, 256>>>(p->U<float>(p->cur), g, stage, lo, hi - lo);
+        unpack_kernel<float><<<p->sm_count * 8, 256>>>(pick(float{}), g, stage, lo, hi - lo);
     APDE_CUDA(cudaGetLastError());
     APDE_CUDA(cudaMemcpyAsync(out + (size_t)(lo - win_lo) * g.cols, stage, nrow * g.cols * 8, cudaMemcpyDeviceToHost, 0));
     if (wait) APDE_CUDA(cudaStreamSynchronize(0));
@@ -601,6 +613,13 @@ int plan_energy_sums(apde_plan *p, double *sum_h2, double *sum_v2, cudaStream_t 
 // ------------------------------------------------------------------------------------------
 // one-shot host-buffer solve
 // ------------------------------------------------------------------------------------------
+// Fused depth the one-shot solves use when the caller passes temporal_depth <= 0: the measured best per
+// variant on B200 (profiles/).
+int default_temporal_depth(int elem, bool noise) {
+    (void)elem;
+    return noise ? 2 : 3;
+}
+
 static apde_plan *g_cached_plan = nullptr;  // never destroyed at exit (the context may be gone by then)
 
 void release_cached_plan() {
@@ -620,7 +639,7 @@ int solve_redblack(int elem, double *grid, const double *nh, const double *nv, c
         return APDE_OK;
     }
     if (check_every <= 0) check_every = 32;
-    if (temporal_depth <= 0) temporal_depth = nh ? 2 : 3;  // measured best fused depth per variant
+    if (temporal_depth <= 0) temporal_depth = default_temporal_depth(elem, nh != nullptr);
     temporal_depth = std::min(temporal_depth, 4);
     if (rows < 3 || cols < 3) {
         const int64_t n = (0.0 < tol) ? std::min<int64_t>(check_every, max_iter) : max_iter;
@@ -711,12 +730,22 @@ int solve_redblack_multi(int elem, double *grid, const double *nh, const double 
                          int temporal_depth, int n_gpus, double *hist, int64_t *iters, double *ksec) {
     if (ksec) *ksec = 0.0;
     if (check_every <= 0) check_every = 32;
-    if (temporal_depth <= 0) temporal_depth = nh ? 2 : 3;
+    if (temporal_depth <= 0) temporal_depth = default_temporal_depth(elem, nh != nullptr);
     temporal_depth = std::min(temporal_depth, 4);
-    int have = 0;
-    if (cudaGetDeviceCount(&have) != cudaSuccess) have = 0;
-    cudaGetLastError();
-    int ndev = std::min(n_gpus, have);
+    // the sm_100 devices of the box, by ordinal (what apde_device_count counts)
+    std::vector<int> devs;
+    {
+        int have = 0;
+        if (cudaGetDeviceCount(&have) != cudaSuccess) have = 0;
+        cudaGetLastError();
+        for (int d = 0; d < have; ++d) {
+            int major = 0;
+            if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10)
+                devs.push_back(d);
+        }
+        cudaGetLastError();
+    }
+    int ndev = std::min<int>(n_gpus, (int)devs.size());
     const int64_t halo = 2 * (int64_t)temporal_depth;
     while (ndev > 1 && rows / ndev < std::max<int64_t>(halo, 8)) --ndev;  // strips must be thicker than their halo
     if (ndev <= 1 || max_iter <= 0 || rows < 3 || cols < 3)
@@ -724,6 +753,7 @@ int solve_redblack_multi(int elem, double *grid, const double *nh, const double 
                               hist, iters, ksec);
     int dev0 = 0;
     APDE_CUDA(cudaGetDevice(&dev0));
+    release_cached_plan();  // the single-GPU workspace (several GB on dev0) would only be in the way
     struct Strip {
         apde_plan *plan = nullptr;
         cudaStream_t st = nullptr;
@@ -732,7 +762,7 @@ int solve_redblack_multi(int elem, double *grid, const double *nh, const double 
     std::vector<Strip> sp((size_t)ndev);
     auto cleanup = [&]() {
         for (int g = 0; g < ndev; ++g) {
-            cudaSetDevice(g);
+            cudaSetDevice(devs[g]);
             if (sp[g].halo_sent) cudaEventDestroy(sp[g].halo_sent);
             if (sp[g].t0) cudaEventDestroy(sp[g].t0);
             if (sp[g].t1) cudaEventDestroy(sp[g].t1);
@@ -759,11 +789,13 @@ int solve_redblack_multi(int elem, double *grid, const double *nh, const double 
         }                                                                                          \
     } while (0)
     for (int g = 0; g < ndev; ++g) {
-        MG_CUDA(cudaSetDevice(g));
-        for (int o = g - 1; o <= g + 1; o += 2) {  // direct NVLink stores where the topology allows
+        MG_CUDA(cudaSetDevice(devs[g]));
+        // direct NVLink copies where the topology allows; peer access stays enabled for the life of the
+        // process (enabling is idempotent and other plans of this process may rely on it)
+        for (int o = g - 1; o <= g + 1; o += 2) {
             int can = 0;
-            if (o >= 0 && o < ndev && cudaDeviceCanAccessPeer(&can, g, o) == cudaSuccess && can) {
-                cudaError_t e = cudaDeviceEnablePeerAccess(o, 0);
+            if (o >= 0 && o < ndev && cudaDeviceCanAccessPeer(&can, devs[g], devs[o]) == cudaSuccess && can) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(devs[o], 0);
                 if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
                 cudaGetLastError();
             }
@@ -778,6 +810,9 @@ int solve_redblack_multi(int elem, double *grid, const double *nh, const double 
         d.row_begin = rows * g / ndev;
         d.row_end = rows * (g + 1) / ndev;
         MG_TRY(plan_create(&sp[g].plan, &d));
+        // only the ping-pong streaming kernel keeps the ghost rows a neighbour pushes into out of the
+        // running pass's reach; the in-place per-colour variant (APDE_RB_VARIANT=v0) would race
+        sp[g].plan->variant = 1;
         MG_CUDA(cudaStreamCreateWithFlags(&sp[g].st, cudaStreamNonBlocking));
         MG_CUDA(cudaEventCreateWithFlags(&sp[g].halo_sent, cudaEventDisableTiming));
         MG_CUDA(cudaEventCreate(&sp[g].t0));
@@ -785,7 +820,7 @@ int solve_redblack_multi(int elem, double *grid, const double *nh, const double 
         MG_TRY(plan_upload_rows_impl(sp[g].plan, 0, rows, grid, nh, nv, src, false));  // queued, not waited for
     }
     for (int g = 0; g < ndev; ++g) {
-        MG_CUDA(cudaSetDevice(g));
+        MG_CUDA(cudaSetDevice(devs[g]));
         MG_CUDA(cudaStreamSynchronize(0));
     }
     int64_t done = 0;
@@ -795,20 +830,20 @@ int solve_redblack_multi(int elem, double *grid, const double *nh, const double 
     while (done < max_iter && !stop) {
         const int64_t n = std::min<int64_t>(check_every, max_iter - done);
         for (int g = 0; g < ndev; ++g) {
-            MG_CUDA(cudaSetDevice(g));
+            MG_CUDA(cudaSetDevice(devs[g]));
             MG_CUDA(cudaEventRecord(sp[g].t0, sp[g].st));
         }
         for (int64_t k = 0; k < n; k += temporal_depth) {
             const int64_t m = std::min<int64_t>(temporal_depth, n - k);
             for (int g = 0; g < ndev; ++g) {
-                MG_CUDA(cudaSetDevice(g));
+                MG_CUDA(cudaSetDevice(devs[g]));
                 // the ghost rows this pass reads were written by the neighbours' previous halo pushes
                 if (g > 0) MG_CUDA(cudaStreamWaitEvent(sp[g].st, sp[g - 1].halo_sent, 0));
                 if (g + 1 < ndev) MG_CUDA(cudaStreamWaitEvent(sp[g].st, sp[g + 1].halo_sent, 0));
                 MG_TRY(plan_run(sp[g].plan, m, done + k, 0, sp[g].st));
             }
             for (int g = 0; g < ndev; ++g) {
-                MG_CUDA(cudaSetDevice(g));
+                MG_CUDA(cudaSetDevice(devs[g]));
                 for (int side = 0; side < 2; ++side) {
                     const int o = side == 0 ? g - 1 : g + 1;
                     if (o < 0 || o >= ndev) continue;
@@ -816,14 +851,14 @@ int solve_redblack_multi(int elem, double *grid, const double *nh, const double 
                     int64_t nb = 0, onb = 0;
                     MG_TRY(plan_halo(sp[g].plan, side, &send, &recv_unused, &nb));
                     MG_TRY(plan_halo(sp[o].plan, 1 - side, &osend_unused, &orecv, &onb));
-                    MG_CUDA(cudaMemcpyPeerAsync(orecv, o, send, g, (size_t)nb, sp[g].st));
+                    MG_CUDA(cudaMemcpyPeerAsync(orecv, devs[o], send, devs[g], (size_t)nb, sp[g].st));
                 }
                 MG_CUDA(cudaEventRecord(sp[g].halo_sent, sp[g].st));
             }
         }
         std::fill(hist + done, hist + done + n, 0.0);
         for (int g = 0; g < ndev; ++g) {
-            MG_CUDA(cudaSetDevice(g));
+            MG_CUDA(cudaSetDevice(devs[g]));
             MG_CUDA(cudaEventRecord(sp[g].t1, sp[g].st));
             MG_TRY(plan_read_residuals(sp[g].plan, done, n, part.data(), sp[g].st));
             for (int64_t k = 0; k < n; ++k)
@@ -837,12 +872,12 @@ int solve_redblack_multi(int elem, double *grid, const double *nh, const double 
         done += n;
     }
     for (int g = 0; g < ndev; ++g) {
-        MG_CUDA(cudaSetDevice(g));
+        MG_CUDA(cudaSetDevice(devs[g]));
         MG_CUDA(cudaStreamSynchronize(sp[g].st));
-        MG_TRY(plan_download_rows_impl(sp[g].plan, 0, rows, grid, false));  // all devices copy back concurrently
+        MG_TRY(plan_download_rows_impl(sp[g].plan, 0, 0, rows, grid, false));  // all devices copy back concurrently
     }
     for (int g = 0; g < ndev; ++g) {
-        MG_CUDA(cudaSetDevice(g));
+        MG_CUDA(cudaSetDevice(devs[g]));
         MG_CUDA(cudaStreamSynchronize(0));
     }
     *iters = done;

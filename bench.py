@@ -1,15 +1,19 @@
 #!/usr/bin/env python3
 """bench.py -- GLUP/s (lattice updates per second) of the relaxation hot path on B200.
 
-Workload (BASELINE.json configs[3]): 16384 x 16384 Poisson, red-black Gauss-Seidel, fp64 (or
---dtype f32), temporally blocked streaming kernel.  A *step* = `--sweeps` (default 32 = one
-convergence-check interval) full red-black sweeps over the whole grid; inputs are generated on
-the device and stay resident in HBM (2 GiB per array, far larger than the 126 MB L2).
+Headline workload (BASELINE.json configs[3]): 16384 x 16384 Poisson, red-black Gauss-Seidel, fp64,
+temporally blocked streaming kernel.  A *step* = `--sweeps` (default 32 = one convergence-check
+interval) full red-black sweeps over the whole grid; inputs are generated on the device and stay
+resident in HBM (2 GiB per array, far larger than the 126 MB L2).
 N > 1 (torchrun, one rank per GPU): weak scaling -- every rank owns a 16384-row strip of a
 (16384*N) x 16384 grid, halo rows move over NCCL once per fused pass, residual maxima are
-all-reduced at the end of every step.
+all-reduced at the end of every step.  Before the timed region an N > 1 run proves that the strips
+reproduce the single-GPU result bit for bit ("parity").
 
-One JSON line on rank 0; keys per the driver contract (+ roofline, cpu_baseline, e2e, clocks).
+One JSON line on rank 0; keys per the driver contract (+ roofline, cpu_baseline, e2e, clocks, parity,
+variants).  "variants" are the other BASELINE configs measured in the same run: fp32, fp64/fp32 with
+1 % mismatch, config 3 (4096^2 exact wavefront, K = 1000 / 100) at N = 1, and config 5 (65536^2 Poisson
++ mismatch, strong scaling) at N > 1.
 
 --impl reference : the reference algorithm (lexicographic Gauss-Seidel, solver.py:344-368
 upstream) timed on the host cores through the pinned C port under oracle/ (the reference itself
@@ -48,7 +52,8 @@ def parse_args():
     ap.add_argument("--rows", type=int, default=16384, help="rows per GPU")
     ap.add_argument("--cols", type=int, default=16384)
     ap.add_argument("--sweeps", type=int, default=32, help="sweeps per step")
-    ap.add_argument("--depth", type=int, default=int(os.environ.get("APDE_TEMPORAL_DEPTH", "0")), help="fused sweeps per HBM pass (0 = measured best: 3, or 2 with mismatch)")
+    ap.add_argument("--depth", type=int, default=int(os.environ.get("APDE_TEMPORAL_DEPTH", "0")),
+                    help="fused sweeps per HBM pass (0 = the library's measured best for the variant)")
     ap.add_argument("--noise", type=float, default=0.0, help="link mismatch sigma (0 = Poisson, no mismatch)")
     ap.add_argument("--no-source", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
@@ -57,10 +62,24 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    args = ap.parse_args()
-    if args.depth <= 0:
-        args.depth = 2 if args.noise > 0 else 3
-    return args
+    ap.add_argument("--no-variants", action="store_true", help="skip the other BASELINE configs")
+    ap.add_argument("--no-parity", action="store_true", help="skip the N > 1 bitwise self-check")
+    ap.add_argument("--variant-steps", type=int, default=6)
+    return ap.parse_args()
+
+
+def default_depth(dtype: str, noise: bool) -> int:
+    """The fused depth the library picks for a one-shot solve of this variant (apde.h)."""
+    from analog_pde_solver import _backend
+    return _backend.default_temporal_depth(dtype, noise)
+
+
+def host_threads() -> int:
+    """Cores this process may run on -- NOT OpenMP's default, which torchrun pins to 1 (OMP_NUM_THREADS)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -126,12 +145,12 @@ class ClockSampler:
 # CPU legs (oracle = test/bench infrastructure; never on the product path)
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_sample(budget_s: float, with_noise: bool, with_source: bool):
-    """Reference algorithm (lexicographic GS) on the host cores via the pinned C port, all threads.
-    Bounded sample of the bench workload: a 4096 x 4096 tile of the same problem, as many sweeps as
-    fit the budget.  Returns (GLUP/s, cores, description)."""
+    """Reference algorithm (lexicographic GS) on the host cores via the pinned C port, every core this
+    process may use.  Bounded sample of the bench workload: a 4096 x 4096 tile of the same problem, as
+    many sweeps as fit the budget.  Returns (GLUP/s, cores, description)."""
     import oracle
     n = 4096
-    threads = oracle.max_threads()
+    threads = host_threads()
     rng = np.random.default_rng(0)
     g0 = np.zeros((n, n))
     h = 1.0 / (16384 - 1)
@@ -151,7 +170,10 @@ def cpu_reference_sample(budget_s: float, with_noise: bool, with_source: bool):
     t0 = time.perf_counter()
     oracle.gauss_seidel_mt(g0, nh, nv, src, sweeps, threads)
     dt = time.perf_counter() - t0
-    return lups * sweeps / dt / 1e9, threads, f"{n}x{n} tile of the workload, {sweeps} lexicographic sweeps, {threads} threads (C port of solver.py:344-368, bit-identical to the reference)"
+    return lups * sweeps / dt / 1e9, threads, (
+        f"{n}x{n} tile of the workload, {sweeps} lexicographic sweeps, {threads} threads = every core of the "
+        f"process's affinity mask (OMP_NUM_THREADS={os.environ.get('OMP_NUM_THREADS', 'unset')} is overridden); "
+        "C port of solver.py:344-368, bit-identical to the reference")
 
 
 def run_reference(args):
@@ -167,6 +189,8 @@ def run_reference(args):
         if k >= args.warmup:
             vals.append(v)
     value = statistics.mean(vals)
+    if args.depth <= 0:
+        args.depth = default_depth(args.dtype, args.noise > 0)
     out = {
         "impl": "reference", "metric": "GLUP/s", "value": value, "unit": "GLUP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
@@ -193,62 +217,226 @@ def workload_config(args, world):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    from analog_pde_solver import _backend
+class Ctx:
+    """Process-wide handles of one bench run."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.dist = None
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.dist = dist
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        self.peak = float(peaks.get("hbm_gbs", 6650.0))
+        self.peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        try:  # DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` captures
+            self.traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        except Exception:
+            self.traffic = {}
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x: float) -> float:
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def make_solver(ctx, grows, cols, dtype, noise, has_src, depth, seed=1234):
     from analog_pde_solver.strips import CudaStripEngine, StripSolver, partition_rows
+    dt = np.float64 if dtype == "f64" else np.float32
+    begin, end = partition_rows(grows, ctx.world)[ctx.rank]
+    eng = CudaStripEngine(grows, cols, begin, end, dtype=dt, has_noise=noise > 0, has_source=has_src,
+                          temporal_depth=depth)
+    eng.plan.fill(kind=1 if has_src else 0, top_hot=not has_src, noise_level=noise, seed=seed)
+    return eng, StripSolver(eng, ctx.rank, ctx.world, depth, ctx.dist), (begin, end)
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    dt = np.float64 if args.dtype == "f64" else np.float32
-    has_noise, has_src = args.noise > 0, not args.no_source
-    grows = args.rows * world
-    begin, end = partition_rows(grows, world)[rank]
-    eng = CudaStripEngine(grows, args.cols, begin, end, dtype=dt, has_noise=has_noise,
-                          has_source=has_src, temporal_depth=args.depth)
-    eng.plan.fill(kind=1 if has_src else 0, top_hot=not has_src, noise_level=args.noise, seed=1234)
-    solver = StripSolver(eng, rank, world, args.depth, dist if world > 1 else None)
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+def time_steps(ctx, eng, solver, sweeps, warmup, steps, sampler=None):
+    """W untimed + K timed steps, bracketed by barrier + synchronize, CUDA events on the launching stream,
+    max over ranks.  Returns (ms total, launches inside the timed region, last residuals)."""
+    torch = ctx.torch
 
     def step():
         first = solver.sweeps_done
-        solver.run(args.sweeps)
-        return solver.residuals(first, args.sweeps)  # device->host read of the step's result
+        solver.run(sweeps)
+        return solver.residuals(first, sweeps)  # device->host read of the step's result
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
-    barrier()
-    sampler.mark_begin()
+    ctx.barrier()
+    if sampler:
+        sampler.mark_begin()
     l0 = eng.plan.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for _ in range(args.steps):
+    res = None
+    for _ in range(steps):
         res = step()
     ev1.record()
-    barrier()
-    sampler.mark_end()
-    ms = ev0.elapsed_time(ev1)
-    launches = eng.plan.launches - l0
+    ctx.barrier()
+    if sampler:
+        sampler.mark_end()
+    return ctx.max_over_ranks(ev0.elapsed_time(ev1)), eng.plan.launches - l0, res
+
+
+def roofline_of(ctx, dtype, noise, has_src, depth, rows_per_gpu, cols, glups_per_gpu, avg_launch_ms, single=None):
+    bpl = BYTES_PER_LUP[(dtype, noise > 0, has_src)]
+    achieved = glups_per_gpu * bpl  # GB/s of algorithmic bytes per GPU
+    key = f"{dtype}_d{depth}_noise{int(noise > 0)}_src{int(has_src)}_{rows_per_gpu}x{cols}"
+    tr = ctx.traffic.get(key, {})
+    out = {"bound": "hbm", "achieved": achieved, "peak": ctx.peak, "unit": "GB/s", "frac": achieved / ctx.peak,
+           "traffic": tr.get("dram_bytes_per_launch"),
+           "traffic_source": tr.get("source", "no ncu capture committed for this variant"),
+           "peak_kind": ctx.peak_kind, "kernel": tr.get("kernel", "rb_pipe_kernel / rb_stream_kernel"),
+           "algorithmic_bytes_per_lup": bpl,
+           "algorithmic_bytes_per_launch": bpl * (rows_per_gpu - 2) * (cols - 2) * depth,
+           "avg_launch_ms": avg_launch_ms,
+           "note": "algorithmic bytes = one read+write of u (+source/links) per sweep; the kernel fuses "
+                   f"{depth} sweeps per HBM pass, so frac may exceed 1 while DRAM traffic (ncu, profiles/) stays below peak"}
+    if tr.get("dram_bytes_per_launch") and avg_launch_ms:
+        out["dram_gbs"] = tr["dram_bytes_per_launch"] / (avg_launch_ms * 1e-3) / 1e9
+        out["dram_frac_of_peak"] = out["dram_gbs"] / ctx.peak
+    if single is not None:
+        out["single_sweep_launches"] = {
+            "glups": single, "achieved": single * bpl, "frac": single * bpl / ctx.peak,
+            "note": "same kernel, one sweep per launch (no temporal blocking): every launch moves the algorithmic bytes through HBM"}
+    return out
+
+
+def parity_check(ctx):
+    """N > 1: the strips (NCCL halo exchange, phased overlap) against ONE plan on rank 0, K = 8 sweeps of an
+    (8192*N) x 4096 Poisson + 1 % mismatch problem: position-weighted 64-bit checksums of the owned rows add
+    up (mod 2^64) to the single plan's, and the MAX-all-reduced residuals equal its residuals bit for bit."""
+    from analog_pde_solver import _backend
+    torch = ctx.torch
+    k, cols, depth = 8, 4096, 3
+    grows = 8192 * ctx.world
+    out = {"sweeps": k, "grid": f"{grows}x{cols}", "temporal_depth": depth, "dtypes": {}}
+    ok_all = True
+    for dtype in ("f64", "f32"):
+        eng, solver, _ = make_solver(ctx, grows, cols, dtype, 0.01, True, depth, seed=99)
+        solver.run(k)
+        res = solver.residuals(0, k)
+        bits = eng.plan.checksum_bits(eng.stream())
+        eng.close()
+        # sum mod 2^64 over ranks, as two 32-bit halves so no signed overflow is involved
+        t = torch.tensor([bits & 0xFFFFFFFF, bits >> 32], dtype=torch.int64, device="cuda")
+        ctx.dist.all_reduce(t, op=ctx.dist.ReduceOp.SUM)
+        lo, hi = (int(x) for x in t.tolist())
+        total = (lo + (hi << 32)) % (1 << 64)
+        ok = True
+        if ctx.rank == 0:
+            dt = np.float64 if dtype == "f64" else np.float32
+            with _backend.Plan(grows, cols, dtype=dt, has_noise=True, has_source=True, temporal_depth=depth) as whole:
+                whole.fill(kind=1, top_hot=False, noise_level=0.01, seed=99)
+                done = 0
+                while done < k:
+                    n = min(depth, k - done)
+                    whole.run(n, done)
+                    done += n
+                ref_bits = whole.checksum_bits()
+                ref_res = whole.residuals(0, k)
+            ok = (ref_bits == total) and (ref_res.tobytes() == res.tobytes())
+            out["dtypes"][dtype] = {"checksum_strips": f"{total:016x}", "checksum_single": f"{ref_bits:016x}",
+                                    "residuals_equal": ref_res.tobytes() == res.tobytes()}
+        flag = torch.tensor([1 if ok else 0], device="cuda")
+        ctx.dist.all_reduce(flag, op=ctx.dist.ReduceOp.MIN)
+        ok_all = ok_all and bool(flag.item())
+    out["multi_gpu_bitwise"] = ok_all
+    return out
+
+
+def rb_variant(ctx, name, dtype, grows, cols, noise, has_src, args, scaling):
+    """One red-black configuration measured like the headline (device-resident, K timed steps)."""
+    depth = default_depth(dtype, noise > 0)
+    eng, solver, (begin, end) = make_solver(ctx, grows, cols, dtype, noise, has_src, depth)
+    ms, launches, res = time_steps(ctx, eng, solver, args.sweeps, 2, args.variant_steps)
+    eng.close()
+    glups = (grows - 2) * (cols - 2) * args.sweeps * args.variant_steps / (ms * 1e-3) / 1e9
+    return {"name": name, "metric": "GLUP/s", "value": glups, "unit": "GLUP/s", "n_gpus": ctx.world, "dtype": dtype,
+            "scaling": scaling, "steps": args.variant_steps, "ms_per_step": ms / args.variant_steps,
+            "gpu_launches": int(launches), "last_residual": float(res[-1]),
+            "config": {"workload": f"{grows}x{cols} {'Poisson' if has_src else 'Laplace'}"
+                                   f"{f' + {noise:g} mismatch (device Philox links)' if noise > 0 else ''}, red-black {dtype}, "
+                                   f"{args.sweeps} sweeps/step, temporal depth {depth}",
+                       "rows_per_gpu": end - begin, "temporal_depth": depth},
+            "roofline": roofline_of(ctx, dtype, noise, has_src, depth, end - begin, cols, glups / ctx.world,
+                                    ms / max(launches, 1))}
+
+
+def exact_variant(ctx, k):
+    """BASELINE config 3: 4096^2 Laplace, 1 % mismatch drawn by numpy exactly as the reference does
+    (solver.py:201-213), fp64 bit-exact wavefront path, K sweeps (tol = 0), through the one-shot C-ABI call."""
+    from analog_pde_solver import AnalogPDESolver, _backend
+    n = 4096
+    s = AnalogPDESolver(rows=n, cols=n, noise_level=0.01, rng_seed=0)
+    g0 = np.zeros((n, n))
+    g0[0, :] = 1.0
+    best_k, best_w = 1e30, 1e30
+    for _ in range(2):
+        g = g0.copy()
+        t0 = time.perf_counter()
+        hist, it, ksec = _backend.solve("exact", g, s._noise_h, s._noise_v, None, 0.0, k)
+        best_w = min(best_w, time.perf_counter() - t0)
+        best_k = min(best_k, ksec)
+    lups = (n - 2) * (n - 2) * k
+    glups = lups / best_k / 1e9
+    bpl = 32
+    return {"name": f"config3_exact_4096_mismatch_K{k}", "metric": "GLUP/s", "value": glups, "unit": "GLUP/s",
+            "n_gpus": 1, "dtype": "f64", "sweeps": k, "kernel_ms": best_k * 1e3,
+            "e2e": {"value": lups / best_w / 1e9, "unit": "GLUP/s",
+                    "note": "apde_solve_exact_f64 from host arrays: upload + layout transform + K sweeps + download"},
+            "last_residual": float(hist[-1]),
+            "config": {"workload": f"{n}x{n} Laplace + 0.01 mismatch (numpy default_rng(0) links uploaded), "
+                                   f"exact wavefront fp64, K = {k} sweeps"},
+            "roofline": {"bound": "hbm", "achieved": glups * bpl, "peak": ctx.peak, "unit": "GB/s",
+                         "frac": glups * bpl / ctx.peak, "traffic": None, "algorithmic_bytes_per_lup": bpl,
+                         "note": "the exact path is latency/fp64-division bound, not HBM bound (its working set lives in L2); "
+                                 "the fraction is reported for completeness"}}
+
+
+def run_ours(args):
+    ctx = Ctx()
+    torch, world, rank = ctx.torch, ctx.world, ctx.rank
+    from analog_pde_solver import _backend
+    if args.depth <= 0:
+        args.depth = default_depth(args.dtype, args.noise > 0)
+    has_noise, has_src = args.noise > 0, not args.no_source
+    grows = args.rows * world
+
+    parity = None
+    if world > 1 and not args.no_parity:
+        parity = parity_check(ctx)
+        if not parity["multi_gpu_bitwise"]:
+            if rank == 0:
+                print(json.dumps({"error": "multi-GPU strips differ from the single-GPU result", "parity": parity}), flush=True)
+            ctx.dist.destroy_process_group()
+            raise SystemExit(3)
+
+    eng, solver, (begin, end) = make_solver(ctx, grows, args.cols, args.dtype, args.noise, has_src, args.depth)
+    sampler = ClockSampler(ctx.local)
+    if rank == 0:
+        sampler.start()
+    ms, launches, res = time_steps(ctx, eng, solver, args.sweeps, args.warmup, args.steps, sampler)
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
     lups_step = (grows - 2) * (args.cols - 2) * args.sweeps
     glups = lups_step * args.steps / (ms * 1e-3) / 1e9
 
@@ -298,7 +486,7 @@ def run_ours(args):
             def e2e_step():
                 _backend.solve(mode, host_u, host_nh, host_nv, host_s, 0.0, K, check_every=32,
                                temporal_depth=args.depth)
-            api = f"apde_solve_redblack_{args.dtype} (one call = upload + {K} sweeps, residuals read back every 32 + download)"
+            api = f"apde_solve_redblack_{args.dtype} (one call = upload + {K} sweeps, residuals checked every 32 + download)"
         else:
             out_host = pin((owned, args.cols))
             d2h = out_host.nbytes + K * 8
@@ -314,65 +502,56 @@ def run_ours(args):
             api = f"apde_plan_upload_rows + {K} sweeps with NCCL halo exchange + residual all-reduce + apde_plan_download_rows"
 
         e2e_step()
-        barrier()
+        ctx.barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
             ts = time.perf_counter()
             e2e_step()
             if os.environ.get("APDE_TRACE"):
                 print(f"[bench] e2e call {time.perf_counter() - ts:.3f} s", file=sys.stderr, flush=True)
-        barrier()
-        wall = time.perf_counter() - t0
-        if os.environ.get("APDE_TRACE"):
-            print(f"[bench] e2e wall {wall:.3f} s for {args.e2e_steps} calls", file=sys.stderr, flush=True)
-        tw = torch.tensor([wall], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
-        e2e = {"value": (grows - 2) * (args.cols - 2) * K * args.e2e_steps / float(tw.item()) / 1e9, "unit": "GLUP/s",
+        ctx.barrier()
+        wall = ctx.max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": (grows - 2) * (args.cols - 2) * K * args.e2e_steps / wall / 1e9, "unit": "GLUP/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "sweeps_per_call": K,
                "note": api + ", host arrays in pinned memory"}
+        del host_u, host_s, host_nh, host_nv
+    eng.close()
+    _backend.load().apde_release_cache()
+
+    # ---- the other BASELINE configs, same run ---------------------------------------------------------
+    variants = []
+    if not args.no_variants:
+        if world == 1:
+            for name, dtype, noise in (("config4_f32", "f32", 0.0), ("config4_f64_mismatch", "f64", 0.01),
+                                       ("config4_f32_mismatch", "f32", 0.01)):
+                variants.append(rb_variant(ctx, name, dtype, args.rows, args.cols, noise, True, args, "weak"))
+            for k in (1000, 100):
+                variants.append(exact_variant(ctx, k))
+        else:
+            # config 5: ONE 65536^2 Poisson + 1 % mismatch problem cut into `world` strips (strong scaling).
+            # fp64 needs 5 x 32 GiB: it fits from N = 2 (86 GiB per GPU); fp32 from N = 1.
+            for name, dtype in (("config5_strong_f64", "f64"), ("config5_strong_f32", "f32")):
+                variants.append(rb_variant(ctx, name, dtype, 65536, 65536, 0.01, True, args, "strong"))
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-        bpl = BYTES_PER_LUP[(args.dtype, has_noise, has_src)]
-        per_gpu_glups = glups / world
-        achieved = per_gpu_glups * bpl  # GB/s of algorithmic bytes per GPU
         n_sweep_launches = max(launches, 1)
-        traffic = None
-        try:  # DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture
-            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-            key = f"{args.dtype}_d{args.depth}_noise{int(has_noise)}_src{int(has_src)}_{args.rows}x{args.cols}"
-            traffic = tr.get(key, {}).get("dram_bytes_per_launch")
-        except Exception:
-            pass
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "peak_kind": peak_kind, "kernel": "rb_stream_kernel",
-                    "algorithmic_bytes_per_lup": bpl,
-                    "algorithmic_bytes_per_launch": bpl * (args.rows - 2) * (args.cols - 2) * args.depth,
-                    "avg_launch_ms": ms / n_sweep_launches,
-                    "single_sweep_launches": None if single is None else {
-                        "glups": single, "achieved": single * bpl, "frac": single * bpl / peak,
-                        "note": "same kernel, one sweep per launch (no temporal blocking): every launch moves the algorithmic bytes through HBM"},
-                    "note": "algorithmic bytes = one read+write of u (+source/links) per sweep; the kernel fuses "
-                            f"{args.depth} sweeps per HBM pass, so frac may exceed 1 while DRAM traffic (ncu, profiles/) stays below peak"}
+        roofline = roofline_of(ctx, args.dtype, args.noise, has_src, args.depth, args.rows, args.cols, glups / world,
+                               ms / n_sweep_launches, single)
         out = {"metric": "GLUP/s", "value": glups, "unit": "GLUP/s", "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": args.dtype, "data": "synthetic (device-generated sin source, zero ring)",
                "config": workload_config(args, world), "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches),
                "clocks": clocks, "last_residual": float(res[-1])}
+        if parity is not None:
+            out["parity"] = parity
+        if variants:
+            out["variants"] = variants
         if world == 1 and not args.no_cpu_baseline:
             v, cores, desc = cpu_reference_sample(args.cpu_seconds, has_noise, has_src)
             out["cpu_baseline"] = {"value": v, "unit": "GLUP/s", "cores": cores, "kind": "port", "sample": desc}
         print(json.dumps(out), flush=True)
-    eng.close()
-    if world > 1:
-        dist.destroy_process_group()
+    if ctx.dist is not None:
+        ctx.dist.destroy_process_group()
 
 
 def main():

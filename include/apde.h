@@ -91,6 +91,9 @@ int apde_solve_redblack_multi(int dtype_bytes, double *grid, const double *noise
                               int64_t max_iter, int check_every, int temporal_depth, int n_gpus,
                               double *residual_history, int64_t *iterations_run, double *kernel_seconds);
 
+/* The fused depth the one-shot solves use for temporal_depth <= 0 (dtype_bytes 8 / 4, with or without mismatch). */
+int apde_default_temporal_depth(int dtype_bytes, int has_noise);
+
 /* The red-black one-shot solves keep their device workspace for the next call of the same shape
  * (allocation of several GB costs 10-100 ms); this frees it.  APDE_NO_PLAN_CACHE=1 disables the cache. */
 int apde_release_cache(void);
@@ -138,6 +141,10 @@ int apde_plan_upload_rows(apde_plan *plan, int64_t row_lo, int64_t row_hi, const
                           const double *noise_h, const double *noise_v, const double *source);
 /* Copy the owned rows that fall inside [row_lo, row_hi) into `out`, which holds exactly that window. */
 int apde_plan_download_rows(apde_plan *plan, int64_t row_lo, int64_t row_hi, double *out);
+/* Same for any of the plan's arrays, as float64: which 0 = current grid, 1 = source (h^2 f), 2 = gh, the
+ * conductance 1/noise_h of link (i,j)-(i,j+1) (0 in the last column), 3 = gv, 1/noise_v of link
+ * (i,j)-(i+1,j) (0 in the last row).  Lets a caller read back inputs that apde_plan_fill generated. */
+int apde_plan_download_array(apde_plan *plan, int which, int64_t row_lo, int64_t row_hi, double *out);
 /* Generate inputs on the device. */
 int apde_plan_fill(apde_plan *plan, const apde_fill_desc *fill);
 /* Copy this strip's owned rows into a GLOBAL host float64 grid. */

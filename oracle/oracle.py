@@ -122,7 +122,7 @@ def reciprocal_links(noise: np.ndarray, dtype) -> np.ndarray:
 
 
 def red_black(grid, noise_h=None, noise_v=None, source=None, n_sweeps: int = 1,
-              dtype=np.float64):
+              dtype=np.float64, conductances=None):
     """Red-black Gauss-Seidel, colour (i+j) even first, fixed sweep count.
 
     The CPU statement of the CUDA throughput kernels' arithmetic (expression tree
@@ -136,7 +136,11 @@ def red_black(grid, noise_h=None, noise_v=None, source=None, n_sweeps: int = 1,
     if (noise_h is None) != (noise_v is None):
         raise ValueError("noise_h and noise_v must be given together")
     gh = gv = None
-    if noise_h is not None:
+    if conductances is not None:
+        # g given directly in the working type (e.g. read back from the device): gh (rows, cols-1), gv (rows-1, cols)
+        gh = _chk(conductances[0], (rows, cols - 1), dtype, "gh")
+        gv = _chk(conductances[1], (rows - 1, cols), dtype, "gv")
+    elif noise_h is not None:
         gh = reciprocal_links(_chk(noise_h, (rows, cols - 1), np.float64, "noise_h"), dtype)
         gv = reciprocal_links(_chk(noise_v, (rows - 1, cols), np.float64, "noise_v"), dtype)
     src = None

@@ -222,6 +222,20 @@ def test_config3_size_4096_mismatch_iterates():
     assert it == k and hist.tobytes() == rh.tobytes() and g.tobytes() == ru.tobytes()
 
 
+def test_config3_size_4096_many_sweeps_in_flight():
+    """Config 3 with more sweeps than the ring has CTA slots (2 x 148 = 296 on B200): K = 420 sweeps,
+    so the ring wraps (CTA c runs sweeps c, c+G, ...) with every slot busy.  Grid and all 420 residuals
+    equal the CPU oracle (column-block pipelined over the host threads, bitwise equal to the serial loop)."""
+    n, k = 4096, 420
+    s = AnalogPDESolver(rows=n, cols=n, noise_level=0.01, rng_seed=0)
+    g0 = np.zeros((n, n))
+    g0[0, :] = 1.0
+    ru, rh, _ = oracle.gauss_seidel_mt(g0, s._noise_h, s._noise_v, None, k)
+    g = g0.copy()
+    hist, it, _ = _backend.solve("exact", g, s._noise_h, s._noise_v, None, 0.0, k)
+    assert it == k and hist.tobytes() == rh.tobytes() and g.tobytes() == ru.tobytes()
+
+
 def test_poisson_demo_numbers():
     """What examples/poisson_demo.py upstream prints (20 x 20) and BASELINE config 2 (64 x 64)."""
     from helpers import zero_boundary, sin_source

@@ -154,11 +154,15 @@ def test_plan_two_strips_equal_one_strip_bitwise():
         assert hist.tobytes() == ref_hist.tobytes()
 
 
+@pytest.mark.parametrize("cuts", [[0, 70, 150, 230], [0, 70, 153, 230], [0, 65, 132, 230]])
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
-def test_three_strips_phased_overlap_protocol(dt, monkeypatch):
+def test_three_strips_phased_overlap_protocol(dt, cuts, monkeypatch):
     """The multi-GPU schedule of analog_pde_solver/strips.py on one GPU: per group, phase 1 (row blocks
     next to a neighbour) -> halo copies out of the half-written buffer -> phase 2 (interior blocks).
-    Three plans stand in for three ranks; result must equal the single-strip run bit for bit."""
+    Three plans stand in for three ranks; result must equal the single-strip run bit for bit.
+    The cuts include strips whose height is 1..halo-1 rows more than a multiple of the row block (83 = 5*16+3,
+    67 = 4*16+3): the rows the halo exchange ships then straddle the last two row blocks, both of which must
+    run in phase 1."""
     monkeypatch.setenv("APDE_ROW_BLOCK", "16")
     rows, cols, depth = 230, 140, 3
     groups = [3, 3, 2, 1]
@@ -173,7 +177,6 @@ def test_three_strips_phased_overlap_protocol(dt, monkeypatch):
             base += n
         ref = whole.download()
         ref_hist = whole.residuals(0, sum(groups))
-    cuts = [0, 70, 150, rows]
     plans = [_backend.Plan(rows, cols, cuts[k], cuts[k + 1], **kw) for k in range(3)]
     for p in plans:
         p.upload(g0, nh, nv, s)
@@ -260,3 +263,59 @@ def test_strip_checksums_add_up_to_single_strip():
             p.upload(g0, nh, nv, s)
             parts = (parts + p.checksum_bits()) % (1 << 64)
     assert parts == whole
+
+
+def test_philox_links_distribution_and_placement():
+    """K7: the device-generated mismatch.  gh / gv read back from the plan equal the host statement
+    (tests/philox_ref.py: Philox4x32-10 keyed by the seed, counter = global link id, Box-Muller) to
+    rounding -- device log/sqrt/cospi vs libm -- link by link, i.e. values AND placement; the implied
+    N(0,1) samples of 2 x 10^6 links have the right mean and variance; a strip generates the same
+    values for its rows as the whole-grid plan (ids are global)."""
+    import philox_ref
+    rows = cols = 1000
+    sigma, seed = 0.01, 77
+    with _backend.Plan(rows, cols, dtype=np.float64, has_noise=True, has_source=False, temporal_depth=2) as p:
+        p.fill(kind=0, top_hot=True, noise_level=sigma, seed=seed)
+        gh, gv = p.download_array("gh"), p.download_array("gv")
+    rh, rv = philox_ref.conductances(rows, cols, sigma, seed)
+    assert (gh[:, -1] == 0).all() and (gv[-1] == 0).all()
+    assert np.max(np.abs(gh - rh)) < 1e-13 and np.max(np.abs(gv - rv)) < 1e-13
+    z = np.concatenate([(1.0 / gh[:, :-1] - 1.0).ravel(), (1.0 / gv[:-1] - 1.0).ravel()]) / sigma
+    assert z.size == 2 * rows * (cols - 1)
+    assert abs(z.mean()) < 4 / np.sqrt(z.size) and abs(z.var() - 1.0) < 6 * np.sqrt(2.0 / z.size)
+    assert abs(np.mean(z ** 3)) < 0.02 and abs(np.mean(z ** 4) - 3.0) < 0.05
+    assert abs(np.corrcoef(gh[:-1, :-1].ravel(), gv[:-1, :-1].ravel())[0, 1]) < 0.01  # h and v links independent
+    # fp32 plan: the fp64 value rounded once; a strip of the same global grid: same links
+    with _backend.Plan(rows, cols, 300, 700, dtype=np.float32, has_noise=True, has_source=False, temporal_depth=2) as p:
+        p.fill(kind=0, top_hot=True, noise_level=sigma, seed=seed)
+        sh, sv = p.download_array("gh", 300, 700), p.download_array("gv", 300, 700)
+    assert np.max(np.abs(sh - rh[300:700].astype(np.float32))) <= 1.2e-7
+    assert np.max(np.abs(sv - rv[300:700].astype(np.float32))) <= 1.2e-7
+    # another seed gives other links
+    with _backend.Plan(64, 64, dtype=np.float64, has_noise=True, has_source=False, temporal_depth=1) as p:
+        p.fill(kind=0, noise_level=sigma, seed=seed + 1)
+        assert np.max(np.abs(p.download_array("gh") - philox_ref.conductances(64, 64, sigma, seed)[0])) > 1e-3
+
+
+@pytest.mark.parametrize("noise", [0.0, 0.01])
+def test_full_size_fp64_subblock_equals_oracle(noise):
+    """BASELINE config 4 at full size in fp64 (16384^2 Poisson, without and with 1 % mismatch): after K
+    sweeps (fused depth 3 then the tail) the top-left block of THAT run equals the CPU red-black oracle
+    run on the 2048^2 sub-problem cut from the same device-generated inputs, bit for bit, on every node
+    the sub-problem's artificial south / east edge cannot have reached (red-black information moves at
+    most two nodes per sweep)."""
+    n, sub, k = 16384, 2048, 8
+    with _backend.Plan(n, n, dtype=np.float64, has_noise=noise > 0, has_source=True, temporal_depth=3) as p:
+        p.fill(kind=1, top_hot=True, noise_level=noise, seed=5)
+        u0 = p.download_array("grid", 0, sub)[:, :sub].copy()
+        src = p.download_array("source", 0, sub)[:, :sub].copy()
+        cond = None
+        if noise > 0:
+            cond = (p.download_array("gh", 0, sub)[:, :sub - 1].copy(), p.download_array("gv", 0, sub - 1)[:, :sub].copy())
+        p.run(k, 0)
+        got = p.download_array("grid", 0, sub)[:, :sub]
+        hist = p.residuals(0, k)
+    want, _, _ = oracle.red_black(u0, None, None, src, k, dtype=np.float64, conductances=cond)
+    m = sub - 2 * k - 2
+    assert got[:m, :m].tobytes() == want[:m, :m].tobytes()
+    assert (got[1:m, 1:m] != u0[1:m, 1:m]).any() and np.isfinite(hist).all() and hist[0] > 0

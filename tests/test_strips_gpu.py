@@ -34,10 +34,10 @@ def test_nccl_strips_bitwise_equal_single_gpu():
     assert "STRIPS_CHECK PASS" in r.stdout
 
 
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs at least two sm_100 GPUs (on one GPU the call is the single-GPU solve)")
 @pytest.mark.parametrize("mode,dt", [("redblack", "f64"), ("redblack32", "f32")])
 def test_single_process_multi_gpu_solve_equals_single_gpu(mode, dt):
-    """apde_solve_redblack_multi (one process, CUDA peer copies) == the single-GPU solve bit for bit.
-    With one visible GPU it falls back to the single-GPU path, which keeps the call under test there."""
+    """apde_solve_redblack_multi (one process, CUDA peer copies) == the single-GPU solve bit for bit."""
     import numpy as np
     from helpers import random_problem
     rows, cols = 700, 333
@@ -55,3 +55,15 @@ def test_single_process_multi_gpu_solve_equals_single_gpu(mode, dt):
     ha, na, _ = _backend.solve(mode, a, None, None, s, 1e-4, 4000, check_every=16)
     hb, nb, _ = _backend.solve(mode, b, None, None, s, 1e-4, 4000, check_every=16, n_gpus=4)
     assert na == nb and a.tobytes() == b.tobytes() and ha.tobytes() == hb.tobytes()
+
+
+def test_multi_gpu_call_on_one_gpu_is_the_single_gpu_solve():
+    """n_gpus larger than the box has degrades to the devices present (documented in include/apde.h);
+    on a one-GPU box that is the plain single-GPU solve."""
+    import numpy as np
+    from helpers import random_problem
+    g0, nh, nv, s = random_problem(90, 70, 0.01, seed=4)
+    a, b = g0.copy(), g0.copy()
+    ha, na, _ = _backend.solve("redblack", a, nh, nv, s, 0.0, 9, check_every=4, temporal_depth=2)
+    hb, nb, _ = _backend.solve("redblack", b, nh, nv, s, 0.0, 9, check_every=4, temporal_depth=2, n_gpus=64)
+    assert na == nb == 9 and a.tobytes() == b.tobytes() and ha.tobytes() == hb.tobytes()
