@@ -23,9 +23,12 @@ struct apde_plan {
     apde::DevBuf stage;       // float64 staging for host<->device conversion (grown on demand, reused)
     int cur = 0;
     bool pass_open = false;   // a phase-1 launch wrote part of u[1-cur]; phase 2 completes it and flips
-    int variant = 1;          // 1 = fused streaming kernel (default), 0 = per-colour in-place kernels
+    int variant = 1;          // 2 = sweep-pipelined shared-memory kernel, 1 = register-window streaming kernel,
+                              // 0 = per-colour in-place kernels (cross-check)
     int lane_vectors = 1;     // 16-byte vectors per lane per row in the streaming kernel (1 or 2)
-    int64_t row_block = 256;  // rows per work item of the streaming kernel
+    int64_t row_block = 256;  // rows per work item of the streaming kernel (v2 sizes its blocks itself unless forced)
+    bool row_block_forced = false;  // APDE_ROW_BLOCK was given
+    int64_t edge_rows = 128;  // v2: rows next to a neighbour strip that form the phase-1 row blocks
     int64_t resid_cap = 0;
     int64_t launches = 0;
     bool filled = false;
@@ -58,6 +61,8 @@ int plan_checksum(apde_plan *p, double *sum_out, double *absmax_out, uint64_t *b
 int plan_ensure_resid(apde_plan *p, int64_t cap);
 void release_cached_plan();
 int default_temporal_depth(int elem, bool noise);
+int default_rb_variant();
+int max_temporal_depth();
 int solve_redblack_multi(int elem, double *grid, const double *nh, const double *nv, const double *src,
                          int64_t rows, int64_t cols, double tol, int64_t max_iter, int check_every,
                          int temporal_depth, int n_gpus, double *hist, int64_t *iters, double *ksec);

@@ -82,5 +82,8 @@ inline Geo make_geo(const apde_plan *p) {
 // implemented in apde_rb_stream_f64.cu / apde_rb_stream_f32.cu
 int run_stream_f64(apde_plan *p, int64_t n_sweeps, int64_t sweep_base, int phase, cudaStream_t st);
 int run_stream_f32(apde_plan *p, int64_t n_sweeps, int64_t sweep_base, int phase, cudaStream_t st);
+// implemented in apde_rb_pipe_f64.cu / apde_rb_pipe_f32.cu
+int run_pipe_f64(apde_plan *p, int64_t n_sweeps, int64_t sweep_base, int phase, cudaStream_t st);
+int run_pipe_f32(apde_plan *p, int64_t n_sweeps, int64_t sweep_base, int phase, cudaStream_t st);
 
 }  // namespace apde

@@ -220,6 +220,21 @@ __global__ void energy_kernel(const T *__restrict__ u, Geo g, double *out /*[0]=
 // ------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------
+// Tuning / cross-check knobs from the environment (read at plan creation and whenever a cached plan is reused).
+static void apply_env_knobs(apde_plan *p) {
+    p->variant = default_rb_variant();
+    p->lane_vectors = p->d.dtype_bytes == 8 ? 2 : 1;  // 4 columns per lane for both types (measured best)
+    if (const char *v = getenv("APDE_LANE_VECTORS")) p->lane_vectors = atoi(v) == 2 ? 2 : 1;
+    p->row_block = 256;
+    p->row_block_forced = false;
+    if (const char *v = getenv("APDE_ROW_BLOCK")) {
+        p->row_block = std::max(8, atoi(v));
+        p->row_block_forced = true;
+    }
+    p->edge_rows = 128;
+    if (const char *v = getenv("APDE_EDGE_ROWS")) p->edge_rows = std::max(1, atoi(v));
+}
+
 int plan_create(apde_plan **out, const apde_plan_desc *d) {
     if (!out || !d) {
         set_error("plan_create: NULL argument");
@@ -228,7 +243,7 @@ int plan_create(apde_plan **out, const apde_plan_desc *d) {
     *out = nullptr;
     if ((d->dtype_bytes != 4 && d->dtype_bytes != 8) || d->grows < 1 || d->cols < 1 ||
         d->row_begin < 0 || d->row_end > d->grows || d->row_begin >= d->row_end ||
-        d->temporal_depth < 1 || d->temporal_depth > 4) {
+        d->temporal_depth < 1 || d->temporal_depth > 6) {
         set_error("plan_create: bad descriptor (dtype=%d grows=%lld cols=%lld rows=[%lld,%lld) depth=%d)",
                   d->dtype_bytes, (long long)d->grows, (long long)d->cols, (long long)d->row_begin,
                   (long long)d->row_end, d->temporal_depth);
@@ -264,10 +279,7 @@ int plan_create(apde_plan **out, const apde_plan_desc *d) {
     p->row0 = d->row_begin - p->ghost_top;
     p->padl = 64;  // 512 B (fp64) of zero columns: vector alignment + left tile overhang
     p->pitch = ((p->padl + d->cols + 576 + 63) / 64) * 64;  // right overhang: two of the widest warp strips
-    if (const char *v = getenv("APDE_RB_VARIANT")) p->variant = (v[0] == 'v' ? atoi(v + 1) : atoi(v)) ? 1 : 0;
-    p->lane_vectors = d->dtype_bytes == 8 ? 2 : 1;  // 4 columns per lane for both types (measured best)
-    if (const char *v = getenv("APDE_LANE_VECTORS")) p->lane_vectors = atoi(v) == 2 ? 2 : 1;
-    if (const char *v = getenv("APDE_ROW_BLOCK")) p->row_block = std::max(8, atoi(v));
+    apply_env_knobs(p);
     const size_t bytes = p->plane_elems() * (size_t)p->elem;
     int rc = APDE_OK;
     if ((rc = p->u[0].alloc(bytes)) || (rc = p->u[1].alloc(bytes)) ||
@@ -472,6 +484,8 @@ static int run_v0(apde_plan *p, int64_t n_sweeps, int64_t sweep_base, cudaStream
 
 template <typename T>
 static int run_dispatch(apde_plan *p, int64_t n, int64_t base, int phase, cudaStream_t st) {
+    if (p->variant == 2)
+        return sizeof(T) == 8 ? run_pipe_f64(p, n, base, phase, st) : run_pipe_f32(p, n, base, phase, st);
     if (p->variant == 1)
         return sizeof(T) == 8 ? run_stream_f64(p, n, base, phase, st) : run_stream_f32(p, n, base, phase, st);
     if (phase == 2) return APDE_OK;  // v0 does everything in phase 0/1
@@ -613,6 +627,14 @@ int plan_energy_sums(apde_plan *p, double *sum_h2, double *sum_v2, cudaStream_t 
 // ------------------------------------------------------------------------------------------
 // one-shot host-buffer solve
 // ------------------------------------------------------------------------------------------
+// Kernel family: 2 = sweep-pipelined shared-memory kernel (apde_rb_pipe.inl), 1 = register-window streaming
+// kernel (apde_rb_stream.inl), 0 = per-colour in-place kernels.  APDE_RB_VARIANT=v0|v1|v2 overrides.
+int default_rb_variant() {
+    if (const char *v = getenv("APDE_RB_VARIANT")) return std::min(2, std::max(0, v[0] == 'v' ? atoi(v + 1) : atoi(v)));
+    return 1;
+}
+int max_temporal_depth() { return default_rb_variant() == 2 ? 6 : 4; }
+
 // Fused depth the one-shot solves use when the caller passes temporal_depth <= 0: the measured best per
 // variant on B200 (profiles/).
 int default_temporal_depth(int elem, bool noise) {
@@ -640,7 +662,7 @@ int solve_redblack(int elem, double *grid, const double *nh, const double *nv, c
     }
     if (check_every <= 0) check_every = 32;
     if (temporal_depth <= 0) temporal_depth = default_temporal_depth(elem, nh != nullptr);
-    temporal_depth = std::min(temporal_depth, 4);
+    temporal_depth = std::min(temporal_depth, max_temporal_depth());
     if (rows < 3 || cols < 3) {
         const int64_t n = (0.0 < tol) ? std::min<int64_t>(check_every, max_iter) : max_iter;
         for (int64_t k = 0; k < n; ++k) hist[k] = 0.0;
@@ -671,6 +693,7 @@ int solve_redblack(int elem, double *grid, const double *nh, const double *nv, c
         memcmp(&g_cached_plan->d, &d, sizeof(d)) == 0) {
         p = g_cached_plan;
         g_cached_plan = nullptr;
+        apply_env_knobs(p);
     } else {
         release_cached_plan();
         APDE_TRY(plan_create(&p, &d));
@@ -731,7 +754,7 @@ int solve_redblack_multi(int elem, double *grid, const double *nh, const double 
     if (ksec) *ksec = 0.0;
     if (check_every <= 0) check_every = 32;
     if (temporal_depth <= 0) temporal_depth = default_temporal_depth(elem, nh != nullptr);
-    temporal_depth = std::min(temporal_depth, 4);
+    temporal_depth = std::min(temporal_depth, max_temporal_depth());
     // the sm_100 devices of the box, by ordinal (what apde_device_count counts)
     std::vector<int> devs;
     {
@@ -812,7 +835,7 @@ int solve_redblack_multi(int elem, double *grid, const double *nh, const double 
         MG_TRY(plan_create(&sp[g].plan, &d));
         // only the ping-pong streaming kernel keeps the ghost rows a neighbour pushes into out of the
         // running pass's reach; the in-place per-colour variant (APDE_RB_VARIANT=v0) would race
-        sp[g].plan->variant = 1;
+        if (sp[g].plan->variant == 0) sp[g].plan->variant = 1;
         MG_CUDA(cudaStreamCreateWithFlags(&sp[g].st, cudaStreamNonBlocking));
         MG_CUDA(cudaEventCreateWithFlags(&sp[g].halo_sent, cudaEventDisableTiming));
         MG_CUDA(cudaEventCreate(&sp[g].t0));

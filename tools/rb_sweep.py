@@ -11,10 +11,10 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=16384)
 ap.add_argument("--dtypes", default="f64,f32")
 ap.add_argument("--depths", default="1,2,3,4")
-ap.add_argument("--lanes", default="1,2")
+ap.add_argument("--lanes", default="default")
 ap.add_argument("--noise", default="0")
 ap.add_argument("--src", default="1")
-ap.add_argument("--rowblocks", default="256")
+ap.add_argument("--rowblocks", default="auto")
 ap.add_argument("--sweeps", type=int, default=24)
 a = ap.parse_args()
 n = a.n
@@ -23,8 +23,14 @@ for dt in a.dtypes.split(","):
         for src in [int(x) for x in a.src.split(",")]:
             for lv in a.lanes.split(","):
                 for rb in a.rowblocks.split(","):
-                    os.environ["APDE_LANE_VECTORS"] = lv
-                    os.environ["APDE_ROW_BLOCK"] = rb
+                    if lv == "default":
+                        os.environ.pop("APDE_LANE_VECTORS", None)
+                    else:
+                        os.environ["APDE_LANE_VECTORS"] = lv
+                    if rb == "auto":
+                        os.environ.pop("APDE_ROW_BLOCK", None)
+                    else:
+                        os.environ["APDE_ROW_BLOCK"] = rb
                     for depth in [int(x) for x in a.depths.split(",")]:
                         p = _backend.Plan(n, n, dtype=np.float64 if dt == "f64" else np.float32,
                                           has_noise=bool(noise), has_source=bool(src), temporal_depth=depth)
