@@ -20,12 +20,20 @@
 // lockstep: slot (n & 1) is written in step n and read in step n + 1.
 //
 // What this buys over one-warp-owns-all-sweeps:
-//   * registers per thread no longer grow with TD (the window is 6 rows at any depth): 16+ warps per SM
+//   * registers per thread no longer grow with TD (the window is 6 rows at any depth): 16 warps per SM
 //     instead of 8, dependent chains of two stages instead of 2*TD, depth up to 6;
 //   * the W strips of a tile exchange their edge columns through the shared row slots, so the column halo
 //     that is recomputed is 2*(TD-1) columns per TILE side, not 2*TD per 128-column warp strip;
 //   * u rows enter through cp.async.bulk (SASS UBLKCP) 11 rows ahead and source / conductance rows are pulled
 //     into L2 by cp.async.bulk.prefetch.L2 -- no per-thread prefetch instructions.
+//
+// MEASURED (B200, 16384^2, profiles/r2_pipe_*): bit-exact, but NOT faster than the register-window kernel -- fp64
+// Poisson 314 GLUP/s at depth 4 (v1: 447 at depth 3), Laplace 531 (v1: 736), fp64 + mismatch 188 (v1: 194).  A step
+// hands over only one row (4 nodes per lane), so the per-step costs -- the CTA barrier (37 % of all warp stall
+// samples), fetch / emit / predicate bookkeeping (~120 issued instructions per warp-step, i.e. 30 per node) -- are
+// not amortised; replacing the CTA barrier by per-slot mbarrier pairs (sweeps free to drift) measured 15-25 % slower
+// still, and 2 columns per lane with twice the warps 25 % slower.  The kernel therefore ships as the alternative
+// family APDE_RB_VARIANT=v2 (all tests run on it too); the default stays v1.
 //
 // Arithmetic per node is rb_partial / rb_finish (apde_rb_common.cuh), the same expression tree as every
 // other red-black kernel and the CPU checker, so results are bit-identical across kernels and depths.
@@ -102,7 +110,7 @@ constexpr int PIPE_C = sizeof(T) == 8 ? RBP_C64 : 4;
 #define RBP_WT_PLAIN 16
 #endif
 #ifndef RBP_WT_NOISE
-#define RBP_WT_NOISE 16
+#define RBP_WT_NOISE (sizeof(T) == 8 ? 12 : 16)
 #endif
 __host__ __device__ constexpr int pipe_warp_target(bool noise) { return noise ? RBP_WT_NOISE : RBP_WT_PLAIN; }
 // Column strips per CTA: as many as the warp target allows at this depth, at most what keeps a tile (30*C*W + 2*C
