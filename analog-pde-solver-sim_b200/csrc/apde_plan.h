@@ -30,6 +30,8 @@ struct apde_plan {
     bool row_block_forced = false;  // APDE_ROW_BLOCK was given
     int64_t edge_rows = 128;  // v2: rows next to a neighbour strip that form the phase-1 row blocks
     int64_t resid_cap = 0;
+    const int *stop_flag = nullptr;  // device-visible flag: when non-null and set, every sweep kernel of this plan
+                                     // returns at once (the device-side convergence stop of the one-shot solves)
     int64_t launches = 0;
     bool filled = false;
 

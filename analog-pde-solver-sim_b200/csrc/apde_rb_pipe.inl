@@ -72,6 +72,7 @@ struct PipeArgs {
     T *out;
     const T *src, *gh, *gv;
     T *resid;  // slot of the first sweep of this pass
+    const int *stop;  // optional device flag: set => the solve has converged, do nothing
     long long pitch, padl;
     int lrows, cols;
     long long row0;
@@ -154,6 +155,7 @@ __global__ void __launch_bounds__(PipeGeo<TD, NOISE>::NTHR, PipeGeo<TD, NOISE>::
     constexpr int ROWB = Geo_::ROWB, SLOT = Geo_::SLOT, NTHR = Geo_::NTHR;
     constexpr int PER = 16 / (int)sizeof(T);  // elements per 16-byte vector
 
+    if (a.stop && *a.stop) return;  // device-side stop (uniform over the grid: the flag only changes between launches)
     extern __shared__ __align__(128) unsigned char pipe_smem[];
     const unsigned s_in = ptx::smem_addr(pipe_smem);
     const unsigned s_ring = s_in + DI * SLOT;
@@ -526,6 +528,7 @@ int RBP_FN(apde_plan *p, int64_t n_sweeps, int64_t sweep_base, int phase, cudaSt
         a.gh = p->GH<T>();
         a.gv = p->GV<T>();
         a.resid = p->resid.as<T>() + sweep_base + done;
+        a.stop = p->stop_flag;
         a.pitch = g.pitch;
         a.padl = g.padl;
         a.lrows = (int)g.lrows;

@@ -50,6 +50,7 @@ struct StreamArgs {
     T *out;
     const T *src, *gh, *gv;
     T *resid;  // slot of the first sweep of this pass
+    const int *stop;  // optional device flag: set => the solve has converged, do nothing
     long long pitch, padl, lrows, cols, grows, row0;
     long long own_lo, own_hi;
     long long rbh;                 // row-block height
@@ -218,6 +219,7 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
     constexpr int L2PF = NOISE ? 0 : L2PF_ROWS;
     constexpr int OPF = NOISE ? RBS_OPF : 2 * RBS_OPF;
 
+    if (a.stop && *a.stop) return;  // device-side stop: a sweep after the converged check interval is a no-op
     const int lane = threadIdx.x & 31;
     const long long warp_id = (long long)blockIdx.x * (RBS_THREADS / 32) + (threadIdx.x >> 5);
     const long long n_warps = (long long)gridDim.x * (RBS_THREADS / 32);
@@ -517,6 +519,7 @@ int RBS_FN(apde_plan *p, int64_t n_sweeps, int64_t sweep_base, int phase, cudaSt
         a.gh = p->GH<T>();
         a.gv = p->GV<T>();
         a.resid = p->resid.as<T>() + sweep_base + done;
+        a.stop = p->stop_flag;
         a.pitch = g.pitch;
         a.padl = g.padl;
         a.lrows = g.lrows;

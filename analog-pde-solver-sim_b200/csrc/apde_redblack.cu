@@ -32,7 +32,8 @@ template <typename T, bool NOISE, bool SRC>
 __global__ void __launch_bounds__(256) rb_colour_kernel(T *__restrict__ u, const T *__restrict__ src,
                                                         const T *__restrict__ gh,
                                                         const T *__restrict__ gv, Geo g, int colour,
-                                                        T *resid_slot) {
+                                                        T *resid_slot, const int *stop) {
+    if (stop && *stop) return;
     const long long hw = (g.cols - 1) / 2;
     const long long jj = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     T mx = (T)0;
@@ -214,6 +215,33 @@ __global__ void energy_kernel(const T *__restrict__ u, Geo g, double *out /*[0]=
     if ((threadIdx.x & 31) == 0) {
         atomicAdd(out, sh);
         atomicAdd(out + 1, sv);
+    }
+}
+
+// K6: the convergence decision, on the device.  After the sweeps of one check interval, one thread block looks at
+// the interval's per-sweep maxima (solver.py:283: max_change < tol, strict) and, the first time one is below tol,
+// publishes {stop = 1, intervals = this interval's ordinal} to a status block the host can read without a copy
+// (mapped pinned memory).  Every sweep kernel launched afterwards sees the flag and returns at once, so the host may
+// queue check intervals ahead without ever reading a residual back.
+struct SolveStatus {
+    int stop;        // 1 once an interval has converged
+    int intervals;   // ordinal (1-based) of the interval that converged
+};
+template <typename T>
+__global__ void stop_check_kernel(const T *__restrict__ resid, int n, double tol, int ordinal, int *dev_flag,
+                                  SolveStatus *status) {
+    if (*dev_flag) return;
+    __shared__ int hit;
+    if (threadIdx.x == 0) hit = 0;
+    __syncthreads();
+    for (int k = threadIdx.x; k < n; k += blockDim.x)
+        if ((double)resid[k] < tol) hit = 1;
+    __syncthreads();
+    if (threadIdx.x == 0 && hit) {
+        *dev_flag = 1;  // what the sweep kernels poll (device memory: an L2 hit, not a PCIe read)
+        status->intervals = ordinal;
+        __threadfence_system();
+        status->stop = 1;  // what the host polls
     }
 }
 
@@ -474,7 +502,7 @@ static int run_v0(apde_plan *p, int64_t n_sweeps, int64_t sweep_base, cudaStream
         T *slot = p->resid.as<T>() + sweep_base + s;
         for (int colour = 0; colour < 2; ++colour) {
             rb_colour_kernel<T, NOISE, SRC><<<grid, block, 0, st>>>(u, p->S<T>(), p->GH<T>(),
-                                                                  p->GV<T>(), g, colour, slot);
+                                                                  p->GV<T>(), g, colour, slot, p->stop_flag);
             p->launches++;
         }
     }
@@ -710,24 +738,78 @@ int solve_redblack(int elem, double *grid, const double *nh, const double *nv, c
     } guard{p, use_cache};
     APDE_TRY(plan_upload(p, grid, nh, nv, src));
     const double t_uploaded = now();
+    // ---- sweep loop without host round trips -------------------------------------------------------------
+    // Check intervals are queued up to QUEUE_AHEAD deep; after each one a one-block kernel takes the stop decision
+    // on the device (stop_check_kernel).  The host only watches a status word in mapped pinned memory -- behind an
+    // event of the interval QUEUE_AHEAD back, never behind the newest work -- and stops queueing once it is set; the
+    // intervals already queued past the converged one are no-ops on the device.
+    struct Pinned {
+        SolveStatus *h = nullptr;
+        ~Pinned() {
+            if (h) cudaFreeHost(h);
+        }
+    } pin;
+    APDE_CUDA(cudaHostAlloc((void **)&pin.h, sizeof(SolveStatus), cudaHostAllocMapped));
+    pin.h->stop = 0;
+    pin.h->intervals = 0;
+    SolveStatus *d_status = nullptr;
+    APDE_CUDA(cudaHostGetDevicePointer((void **)&d_status, pin.h, 0));
+    const int64_t n_intervals = (max_iter + check_every - 1) / check_every;
+    APDE_TRY(plan_ensure_resid(p, max_iter));  // never reallocated while kernels are in flight
+    constexpr int QUEUE_AHEAD = 3;
+    struct Ev {
+        cudaEvent_t e[QUEUE_AHEAD] = {};
+        ~Ev() {
+            for (auto x : e)
+                if (x) cudaEventDestroy(x);
+        }
+    } evq;
+    for (auto &x : evq.e) APDE_CUDA(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
     EventPair ev;
     APDE_TRY(ev.init());
-    float total_ms = 0.f;
-    int64_t done = 0;
+    const bool may_stop = tol > 0.0;  // max_change >= 0 is never below a non-positive (or NaN) tol
+    int *dev_flag = reinterpret_cast<int *>(static_cast<char *>(p->scratch.p) + 32);  // bytes 0..23 belong to the checksums
+    APDE_CUDA(cudaMemsetAsync(dev_flag, 0, sizeof(int), 0));
+    p->stop_flag = may_stop ? dev_flag : nullptr;
+    struct ClearFlag {
+        apde_plan *p;
+        ~ClearFlag() { p->stop_flag = nullptr; }
+    } clear_flag{p};
+    std::vector<int> cur_after((size_t)n_intervals + 1, p->cur);
+    APDE_CUDA(cudaEventRecord(ev.a));
+    int64_t queued = 0;
     bool stop = false;
-    while (done < max_iter && !stop) {
-        const int64_t n = std::min<int64_t>(check_every, max_iter - done);
-        APDE_CUDA(cudaEventRecord(ev.a));
-        APDE_TRY(plan_run(p, n, done, 0, 0));
-        APDE_CUDA(cudaEventRecord(ev.b));
-        APDE_TRY(plan_read_residuals(p, done, n, hist + done, 0));
-        float ms = 0.f;
-        APDE_CUDA(cudaEventElapsedTime(&ms, ev.a, ev.b));
-        total_ms += ms;
-        for (int64_t k = 0; k < n; ++k)
-            if (hist[done + k] < tol) stop = true;  // solver.py:283 tested every check_every sweeps
-        done += n;
+    while (queued < n_intervals && !stop) {
+        const int64_t base = queued * check_every, n = std::min<int64_t>(check_every, max_iter - base);
+        APDE_TRY(plan_run(p, n, base, 0, 0));
+        if (may_stop) {
+            if (p->elem == 8)
+                stop_check_kernel<double><<<1, 128>>>(p->resid.as<double>() + base, (int)n, tol, (int)(queued + 1), dev_flag, d_status);
+            else
+                stop_check_kernel<float><<<1, 128>>>(p->resid.as<float>() + base, (int)n, tol, (int)(queued + 1), dev_flag, d_status);
+            p->launches++;
+            APDE_CUDA(cudaEventRecord(evq.e[queued % QUEUE_AHEAD]));
+        }
+        ++queued;
+        cur_after[(size_t)queued] = p->cur;
+        if (may_stop && queued >= QUEUE_AHEAD) {
+            // the interval QUEUE_AHEAD back has been decided once its event has passed (its event slot is the one
+            // the next interval records into)
+            APDE_CUDA(cudaEventSynchronize(evq.e[(queued - QUEUE_AHEAD) % QUEUE_AHEAD]));
+            stop = *(volatile int *)&pin.h->stop != 0;
+        }
     }
+    APDE_CUDA(cudaEventRecord(ev.b));
+    APDE_CUDA(cudaEventSynchronize(ev.b));
+    APDE_CUDA(cudaGetLastError());
+    float total_ms = 0.f;
+    APDE_CUDA(cudaEventElapsedTime(&total_ms, ev.a, ev.b));
+    int64_t done_intervals = queued;
+    if (may_stop && *(volatile int *)&pin.h->stop) done_intervals = pin.h->intervals;
+    p->cur = cur_after[(size_t)done_intervals];  // launches queued past the converged interval did nothing
+    p->pass_open = false;
+    const int64_t done = std::min<int64_t>(done_intervals * check_every, max_iter);
+    APDE_TRY(plan_read_residuals(p, 0, done, hist, 0));  // solver.py:281 -- one copy for the whole history
     *iters = done;
     if (ksec) *ksec = total_ms * 1e-3;
     const double t_swept = now();

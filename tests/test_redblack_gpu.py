@@ -332,3 +332,28 @@ def test_full_size_fp64_subblock_equals_oracle(noise):
     m = sub - 2 * k - 2
     assert got[:m, :m].tobytes() == want[:m, :m].tobytes()
     assert (got[1:m, 1:m] != u0[1:m, 1:m]).any() and np.isfinite(hist).all() and hist[0] > 0
+
+
+@pytest.mark.parametrize("mode,dt", [("redblack", np.float64), ("redblack32", np.float32)])
+@pytest.mark.parametrize("check_every,depth", [(32, 3), (8, 4), (5, 2), (1, 1)])
+def test_device_side_stop_semantics(mode, dt, check_every, depth):
+    """The stop decision is taken on the device after every check interval and later intervals may already be
+    queued (they must be no-ops).  iterations_run = the end of the first interval holding a sweep with
+    max_change < tol (strict, solver.py:283); residual_history has exactly that many entries; the returned grid is
+    bit-identical to a fixed run of that many sweeps (nothing ran past the stop); tol <= 0 never stops."""
+    rows, cols = 70, 90
+    g0, nh, nv, s = random_problem(rows, cols, 0.01, seed=12)
+    tol = 2e-4 if dt == np.float64 else 5e-4
+    g = g0.copy()
+    hist, n, _ = _backend.solve(mode, g, nh, nv, s, tol, 5000, check_every=check_every, temporal_depth=depth)
+    assert 0 < n < 5000 and n % check_every == 0 and len(hist) == n
+    first = int(np.argmax(hist < tol))            # first crossing
+    assert hist[first] < tol and (hist[:first] >= tol).all()
+    assert n == (first // check_every + 1) * check_every
+    fixed = g0.copy()
+    fh, fn, _ = _backend.solve(mode, fixed, nh, nv, s, 0.0, n, check_every=check_every, temporal_depth=depth)
+    assert fn == n and fixed.tobytes() == g.tobytes() and fh.tobytes() == hist.tobytes()
+    # max_iter caps the run when the tolerance is never met; the partial last interval is run in full
+    g = g0.copy()
+    hist, n, _ = _backend.solve(mode, g, nh, nv, s, 1e-300, 37, check_every=check_every, temporal_depth=depth)
+    assert n == 37 and len(hist) == 37
