@@ -29,7 +29,7 @@ EXPORTED_SYMBOLS = (
     "apde_solve_exact_f64", "apde_solve_exact_f64_path", "apde_solve_redblack_f64", "apde_solve_redblack_f32", "apde_solve_redblack_multi", "apde_release_cache",
     "apde_plan_create", "apde_plan_destroy", "apde_plan_upload", "apde_plan_upload_rows", "apde_plan_download_rows", "apde_plan_fill",
     "apde_plan_download", "apde_plan_clear_residuals", "apde_plan_run", "apde_plan_halo", "apde_plan_residuals",
-    "apde_plan_read_residuals", "apde_plan_launch_count", "apde_plan_checksum", "apde_plan_checksum_bits", "apde_memcpy_dtod", "apde_selftest_division", "apde_plan_energy_sums", "apde_plan_download_array", "apde_default_temporal_depth",
+    "apde_plan_read_residuals", "apde_plan_launch_count", "apde_plan_checksum", "apde_plan_checksum_bits", "apde_memcpy_dtod", "apde_selftest_division", "apde_plan_energy_sums", "apde_plan_download_array", "apde_default_temporal_depth", "apde_solve_redblack_ex", "apde_plan_set_relaxation",
 )
 
 
@@ -90,6 +90,11 @@ def load():
     lib.apde_plan_upload_rows.argtypes = [_vp, _i64, _i64, _dp, _dp, _dp, _dp]
     lib.apde_plan_download_rows.restype = ctypes.c_int
     lib.apde_plan_download_rows.argtypes = [_vp, _i64, _i64, _dp]
+    lib.apde_solve_redblack_ex.restype = ctypes.c_int
+    lib.apde_solve_redblack_ex.argtypes = [ctypes.c_int, _dp, _dp, _dp, _dp] + solve_tail + [
+        ctypes.c_int, ctypes.c_double, ctypes.c_int, _dp, _i64p, _dp]
+    lib.apde_plan_set_relaxation.restype = ctypes.c_int
+    lib.apde_plan_set_relaxation.argtypes = [_vp, ctypes.c_double, ctypes.c_int]
     lib.apde_default_temporal_depth.restype = ctypes.c_int
     lib.apde_default_temporal_depth.argtypes = [ctypes.c_int, ctypes.c_int]
     lib.apde_plan_download_array.restype = ctypes.c_int
@@ -149,7 +154,22 @@ def _as_f64(a, shape, name):
 
 
 EXACT_PATHS = {"auto": 0, "small": 1, "ring": 2}
-MODES = ("exact", "redblack", "redblack64", "redblack32")
+MODES = ("exact", "redblack", "redblack64", "redblack32",
+         "redblack_sor", "redblack_sor32", "redblack_kcl", "redblack_kcl32")
+EXTENDED_MODES = {  # mode -> (dtype bytes, normalised conductances, over-relaxed by default)
+    "redblack_sor": (8, False, True), "redblack_sor32": (4, False, True),
+    "redblack_kcl": (8, True, False), "redblack_kcl32": (4, True, False),
+}
+
+
+def optimal_omega(rows: int, cols: int) -> float:
+    """Optimal SOR factor of the 5-point Laplacian on a rows x cols Dirichlet grid:
+    2 / (1 + sqrt(1 - rho^2)) with the Jacobi spectral radius rho = (cos(pi/(rows-1)) + cos(pi/(cols-1))) / 2
+    (= 2 / (1 + sin(pi/(N-1))) on a square grid)."""
+    if rows < 3 or cols < 3:
+        return 1.0
+    rho = 0.5 * (np.cos(np.pi / (rows - 1)) + np.cos(np.pi / (cols - 1)))
+    return float(2.0 / (1.0 + np.sqrt(max(1.0 - rho * rho, 0.0))))
 
 # Sweeps per C call.  The reference accepts any max_iter because its residual list grows lazily
 # (solver.py:262, :281); here the history buffer of one call is max_iter doubles on the host and on the
@@ -158,7 +178,8 @@ MODES = ("exact", "redblack", "redblack64", "redblack32")
 MAX_SWEEPS_PER_CALL = 1 << 20
 
 
-def _solve_once(lib, mode, grid, nh, nv, src, tol, max_iter, check_every, temporal_depth, exact_path, n_gpus):
+def _solve_once(lib, mode, grid, nh, nv, src, tol, max_iter, check_every, temporal_depth, exact_path, n_gpus,
+                omega=None):
     rows, cols = grid.shape
     hist = np.zeros(max(max_iter, 1), dtype=np.float64)
     iters = ctypes.c_int64(0)
@@ -167,6 +188,14 @@ def _solve_once(lib, mode, grid, nh, nv, src, tol, max_iter, check_every, tempor
     if mode == "exact":
         rc = lib.apde_solve_exact_f64_path(*head, _ptr(hist), ctypes.byref(iters), ctypes.byref(ksec),
                                            EXACT_PATHS[exact_path])
+    elif mode in EXTENDED_MODES:
+        elem, kcl, sor = EXTENDED_MODES[mode]
+        if omega is None:
+            omega = optimal_omega(rows, cols) if sor else 1.0
+        if not (0.0 < float(omega) < 2.0):
+            raise ValueError(f"omega must lie in (0, 2), got {omega}")
+        rc = lib.apde_solve_redblack_ex(elem, *head, int(check_every), float(omega), int(kcl), _ptr(hist),
+                                        ctypes.byref(iters), ctypes.byref(ksec))
     elif n_gpus > 1:
         rc = lib.apde_solve_redblack_multi(4 if mode == "redblack32" else 8, *head, int(check_every),
                                            int(temporal_depth), int(n_gpus), _ptr(hist), ctypes.byref(iters),
@@ -187,7 +216,9 @@ def solve(mode: str, grid: np.ndarray, noise_h, noise_v, source, tol: float, max
           omega: Optional[float] = None):
     """One relaxation solve on the GPU.  `grid` (float64, C-order) is updated in place.
 
-    mode: "exact" (bit-exact wavefront, fp64), "redblack" (fp64) or "redblack32" (fp32).
+    mode: "exact" (bit-exact wavefront, fp64), "redblack" (fp64), "redblack32" (fp32), or the extended updates
+    "redblack_sor[32]" (over-relaxation, `omega` defaults to optimal_omega(rows, cols)) and "redblack_kcl[32]"
+    (normalised conductances; `omega` defaults to 1).
     Returns (residual_history ndarray, iterations_run, kernel_seconds).
     """
     lib = load()
@@ -204,13 +235,13 @@ def solve(mode: str, grid: np.ndarray, noise_h, noise_v, source, tol: float, max
     max_iter = int(max_iter)
     if max_iter <= MAX_SWEEPS_PER_CALL:
         hist, n, ksec = _solve_once(lib, mode, grid, nh, nv, src, tol, max_iter, check_every, temporal_depth,
-                                    exact_path, n_gpus)
+                                    exact_path, n_gpus, omega)
         return hist.copy(), n, ksec
     parts, done, ksec_total = [], 0, 0.0
     while done < max_iter:
         chunk = min(MAX_SWEEPS_PER_CALL, max_iter - done)
         hist, n, ksec = _solve_once(lib, mode, grid, nh, nv, src, tol, chunk, check_every, temporal_depth,
-                                    exact_path, n_gpus)
+                                    exact_path, n_gpus, omega)
         parts.append(hist.copy())
         done += n
         ksec_total += ksec
@@ -276,6 +307,10 @@ class Plan:
         out = np.zeros((row_hi - row_lo, self.desc.cols), dtype=np.float64)
         check(self._lib.apde_plan_download_array(self._h, self.ARRAYS[which], int(row_lo), int(row_hi), _ptr(out)))
         return out
+
+    def set_relaxation(self, omega: float = 1.0, normalised: bool = False):
+        """Extended update for the following run() calls (over-relaxation / normalised conductances)."""
+        check(self._lib.apde_plan_set_relaxation(self._h, float(omega), int(bool(normalised))))
 
     def run(self, n_sweeps: int, sweep_base: int = 0, phase: int = 0, stream: int = 0):
         check(self._lib.apde_plan_run(self._h, int(n_sweeps), int(sweep_base), int(phase), _vp(stream)))

@@ -15,6 +15,12 @@ variable ``APDE_MODE``; default ``"exact"``:
                     ``iterations_run`` may differ by a few sweeps; convergence is tested every
                     ``APDE_CHECK_EVERY`` (default 32) sweeps.
 * ``redblack32`` -- the same in fp32.
+* ``redblack_sor`` / ``redblack_sor32`` -- red-black with over-relaxation (keyword-only ``omega=``, default the
+                    optimum for the ideal mesh): O(N) instead of O(N^2) sweeps, same fixed point.
+* ``redblack_kcl`` / ``redblack_kcl32`` -- each node divides by the sum of its own link conductances (Kirchhoff's
+                    current law) instead of the reference's constant 4: convergent at every grid size where the
+                    reference's update diverges with mismatch; a DIFFERENT (physically normalised) fixed point
+                    when links are mismatched, the same one when they are ideal.  ``omega=`` applies too.
 
 ``APDE_GPUS=N`` spreads a red-black solve over N GPUs of the box from this one process (row strips,
 CUDA peer copies); the exact path is sequential along anti-diagonals and always uses one GPU.
@@ -218,7 +224,8 @@ class AnalogPDESolver:
 
     def solve(self, boundary_fn: Union[BoundaryFn, np.ndarray],
               source_fn: Union[None, SourceFn, np.ndarray] = None,
-              tol: float = 1e-6, max_iter: int = 10_000, *, mode: Optional[str] = None) -> np.ndarray:
+              tol: float = 1e-6, max_iter: int = 10_000, *, mode: Optional[str] = None,
+              omega: Optional[float] = None) -> np.ndarray:
         """Relax to ``max_change < tol`` or ``max_iter`` sweeps; returns (and stores) the grid."""
         rows, cols = self.rows, self.cols
         grid = _initial_grid(rows, cols, boundary_fn)
@@ -227,7 +234,7 @@ class AnalogPDESolver:
         # arrays are checked, not the flag, so links edited after construction are honoured like upstream.
         ideal = (not (self.noise_level > 0)) and bool((self._noise_h == 1.0).all() and (self._noise_v == 1.0).all())
         return _relax(self, grid, None if ideal else self._noise_h, None if ideal else self._noise_v,
-                      source, tol, max_iter, _resolve_mode(mode, self.backend_mode))
+                      source, tol, max_iter, _resolve_mode(mode, self.backend_mode), omega)
 
     def energy_joules(self, energy_model: Optional[EnergyModel] = None) -> float:
         model = energy_model or EnergyModel(resistor_ohms=self.resistor_ohms)
@@ -253,7 +260,8 @@ class DigitalSolver:
 
     def solve(self, boundary_fn: Union[BoundaryFn, np.ndarray],
               source_fn: Union[None, SourceFn, np.ndarray] = None,
-              tol: float = 1e-6, max_iter: int = 10_000, *, mode: Optional[str] = None) -> np.ndarray:
+              tol: float = 1e-6, max_iter: int = 10_000, *, mode: Optional[str] = None,
+              omega: Optional[float] = None) -> np.ndarray:
         """Same contract as :meth:`AnalogPDESolver.solve`; also records ``wall_time_s``.
 
         ``wall_time_s`` brackets the relaxation only (host->device copy, kernels, device->host copy),
@@ -263,7 +271,7 @@ class DigitalSolver:
         grid = _initial_grid(rows, cols, boundary_fn)
         source = _source_term(rows, cols, source_fn)
         started = time.perf_counter()
-        _relax(self, grid, None, None, source, tol, max_iter, _resolve_mode(mode, self.backend_mode))
+        _relax(self, grid, None, None, source, tol, max_iter, _resolve_mode(mode, self.backend_mode), omega)
         self.wall_time_s = time.perf_counter() - started
         return grid
 

@@ -141,6 +141,25 @@ int apde_solve_redblack_multi(int dtype_bytes, double *grid, const double *noise
                                 kernel_seconds);
 }
 
+int apde_solve_redblack_ex(int dtype_bytes, double *grid, const double *noise_h, const double *noise_v,
+                           const double *source, int64_t rows, int64_t cols, double tol, int64_t max_iter,
+                           int check_every, double omega, int normalised, double *residual_history,
+                           int64_t *iterations_run, double *kernel_seconds) {
+    APDE_TRY(check_solve_args("apde_solve_redblack_ex", grid, noise_h, noise_v, rows, cols, max_iter,
+                              residual_history, iterations_run));
+    if (dtype_bytes != 4 && dtype_bytes != 8) {
+        set_error("apde_solve_redblack_ex: dtype_bytes must be 4 or 8");
+        return APDE_EINVAL;
+    }
+    std::lock_guard<std::mutex> lock(g_solve_mutex);
+    return solve_redblack(dtype_bytes, grid, noise_h, noise_v, source, rows, cols, tol, max_iter, check_every, 0,
+                          residual_history, iterations_run, kernel_seconds, omega, normalised != 0);
+}
+
+int apde_plan_set_relaxation(apde_plan *plan, double omega, int normalised) {
+    return plan_set_relaxation(plan, omega, normalised);
+}
+
 int apde_default_temporal_depth(int dtype_bytes, int has_noise) {
     return default_temporal_depth(dtype_bytes, has_noise != 0);
 }

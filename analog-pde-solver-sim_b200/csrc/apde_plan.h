@@ -21,6 +21,11 @@ struct apde_plan {
     apde::DevBuf resid;       // per-sweep max_change, plan dtype
     apde::DevBuf scratch;     // checksum outputs etc.
     apde::DevBuf stage;       // float64 staging for host<->device conversion (grown on demand, reused)
+    // extended relaxation: over-relaxation factor and normalised ("KCL") conductance update.
+    // omega == 1 && !kcl is the reference's update and runs on the fused kernels; anything else runs on the
+    // per-colour general kernel.
+    double omega = 1.0;
+    bool kcl = false;
     int cur = 0;
     bool pass_open = false;   // a phase-1 launch wrote part of u[1-cur]; phase 2 completes it and flips
     int variant = 1;          // 2 = sweep-pipelined shared-memory kernel, 1 = register-window streaming kernel,
@@ -70,7 +75,9 @@ int solve_redblack_multi(int elem, double *grid, const double *nh, const double 
                          int temporal_depth, int n_gpus, double *hist, int64_t *iters, double *ksec);
 int solve_redblack(int elem, double *grid, const double *nh, const double *nv, const double *src,
                    int64_t rows, int64_t cols, double tol, int64_t max_iter, int check_every,
-                   int temporal_depth, double *hist, int64_t *iters, double *ksec);
+                   int temporal_depth, double *hist, int64_t *iters, double *ksec, double omega = 1.0,
+                   bool kcl = false);
+int plan_set_relaxation(apde_plan *p, double omega, int normalised);
 // implemented in apde_exact.cu
 int selftest_division(int64_t n, uint64_t seed, int64_t *mismatches);
 int solve_exact_f64(double *grid, const double *nh, const double *nv, const double *src,

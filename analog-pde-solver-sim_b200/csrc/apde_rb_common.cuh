@@ -14,6 +14,7 @@ template <> struct Ar<double> {
     static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
     static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
     static __device__ __forceinline__ double abs(double a) { return fabs(a); }
+    static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
 };
 template <> struct Ar<float> {
     static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
@@ -21,6 +22,7 @@ template <> struct Ar<float> {
     static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
     static __device__ __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
     static __device__ __forceinline__ float abs(float a) { return fabsf(a); }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
 };
 
 // The red-black node update, split so that the operand that arrives last in the streaming kernel's

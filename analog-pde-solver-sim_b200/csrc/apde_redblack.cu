@@ -69,6 +69,63 @@ __global__ void __launch_bounds__(256) rb_colour_kernel(T *__restrict__ u, const
     }
 }
 
+// ==========================================================================================
+// General per-colour kernel: over-relaxation and the normalised ("KCL") update (not in the
+// reference, whose update divides by the constant 4 -- solver.py:269-275 -- and therefore diverges with
+// mismatch once the grid is large, SURVEY finding 2).  The CPU checker of the tests states the same tree (RBX_BODY).
+//   kcl   : scale = 1 / (((gN + gS) + gW) + gE) instead of 0.25
+//   omega : new = fma(omega, gs - old, old)
+// In place, one launch per colour; memory-bound on u + operands, no temporal blocking: these variants buy
+// orders of magnitude in sweep COUNT, not in sweep rate.
+// ==========================================================================================
+template <typename T, bool NOISE, bool SRC>
+__global__ void __launch_bounds__(256) rb_general_kernel(T *__restrict__ u, const T *__restrict__ src,
+                                                         const T *__restrict__ gh, const T *__restrict__ gv, Geo g,
+                                                         int colour, T *resid_slot, const int *stop, T omega, int kcl) {
+    if (stop && *stop) return;
+    const long long hw = (g.cols - 1) / 2;
+    const long long jj = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const bool sor = omega != (T)1;
+    T mx = (T)0;
+    for (long long li = 1 + blockIdx.y; li <= g.lrows - 2; li += gridDim.y) {
+        const long long gi = g.row0 + li;
+        if (gi <= 0 || gi >= g.grows - 1) continue;  // ring rows never move
+        const long long j = 1 + 2 * jj + ((gi + 1 + colour) & 1);
+        if (jj < hw && j <= g.cols - 2) {
+            const long long c = li * g.pitch + g.padl + j;
+            const T un = u[c - g.pitch], us = u[c + g.pitch], uw = u[c - 1], ue = u[c + 1], old = u[c];
+            T tq, gsq, scale = (T)0.25;
+            if (NOISE) {
+                const T gn = gv[c - g.pitch], gs = gv[c], gw = gh[c - 1], ge = gh[c];
+                if (kcl) scale = Ar<T>::div((T)1, Ar<T>::add(Ar<T>::add(Ar<T>::add(gn, gs), gw), ge));
+                tq = Ar<T>::mul(gn, un);
+                tq = Ar<T>::fma(gw, uw, tq);
+                tq = Ar<T>::fma(ge, ue, tq);
+                gsq = Ar<T>::mul(gs, scale);
+            } else {
+                tq = Ar<T>::add(un, uw);
+                tq = Ar<T>::add(tq, ue);
+                gsq = scale;
+            }
+            if (SRC) tq = Ar<T>::sub(tq, src[c]);
+            tq = Ar<T>::mul(tq, scale);
+            T nw = Ar<T>::fma(gsq, us, tq);
+            if (sor) nw = Ar<T>::fma(omega, Ar<T>::sub(nw, old), old);
+            u[c] = nw;
+            if (li >= g.own_lo && li < g.own_hi) mx = max_ignore_nan(mx, Ar<T>::abs(Ar<T>::sub(nw, old)));
+        }
+    }
+    __shared__ T red[8];
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        T v = threadIdx.x < 8 ? red[threadIdx.x] : (T)0;
+        v = warp_max(v);
+        if (threadIdx.x == 0 && v > (T)0) atomic_max_nonneg(resid_slot, v);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // helpers: conversion / reciprocal / fill / checksum
 // ------------------------------------------------------------------------------------------
@@ -510,8 +567,36 @@ static int run_v0(apde_plan *p, int64_t n_sweeps, int64_t sweep_base, cudaStream
     return APDE_OK;
 }
 
+template <typename T, bool NOISE, bool SRC>
+static int run_general(apde_plan *p, int64_t n_sweeps, int64_t sweep_base, cudaStream_t st) {
+    const Geo g = make_geo(p);
+    const long long hw = (g.cols - 1) / 2;
+    if (hw < 1 || g.lrows < 3) return APDE_OK;
+    dim3 block(256);
+    dim3 grid((unsigned)((hw + 255) / 256), (unsigned)std::min<long long>(g.lrows - 2, 32768));
+    T *u = p->U<T>(p->cur);
+    for (int64_t s = 0; s < n_sweeps; ++s) {
+        T *slot = p->resid.as<T>() + sweep_base + s;
+        for (int colour = 0; colour < 2; ++colour) {
+            rb_general_kernel<T, NOISE, SRC><<<grid, block, 0, st>>>(u, p->S<T>(), p->GH<T>(), p->GV<T>(), g, colour, slot,
+                                                                   p->stop_flag, (T)p->omega, p->kcl ? 1 : 0);
+            p->launches++;
+        }
+    }
+    APDE_CUDA(cudaGetLastError());
+    return APDE_OK;
+}
+
 template <typename T>
 static int run_dispatch(apde_plan *p, int64_t n, int64_t base, int phase, cudaStream_t st) {
+    if (p->omega != 1.0 || p->kcl) {
+        if (phase == 2) return APDE_OK;  // in place: everything happens in phase 0/1
+        const bool N = p->d.has_noise, S = p->d.has_source;
+        if (N && S) return run_general<T, true, true>(p, n, base, st);
+        if (N) return run_general<T, true, false>(p, n, base, st);
+        if (S) return run_general<T, false, true>(p, n, base, st);
+        return run_general<T, false, false>(p, n, base, st);
+    }
     if (p->variant == 2)
         return sizeof(T) == 8 ? run_pipe_f64(p, n, base, phase, st) : run_pipe_f32(p, n, base, phase, st);
     if (p->variant == 1)
@@ -550,6 +635,16 @@ int plan_run(apde_plan *p, int64_t n_sweeps, int64_t sweep_base, int phase, cuda
         APDE_CUDA(cudaMemsetAsync((char *)p->resid.p + (size_t)sweep_base * p->elem, 0, (size_t)n_sweeps * p->elem, st));
     return p->elem == 8 ? run_dispatch<double>(p, n_sweeps, sweep_base, phase, st)
                         : run_dispatch<float>(p, n_sweeps, sweep_base, phase, st);
+}
+
+int plan_set_relaxation(apde_plan *p, double omega, int normalised) {
+    if (!p || !(omega > 0.0 && omega < 2.0)) {
+        set_error("plan_set_relaxation: omega must lie in (0, 2), got %g", omega);
+        return APDE_EINVAL;
+    }
+    p->omega = omega;
+    p->kcl = normalised != 0;
+    return APDE_OK;
 }
 
 int plan_clear_residuals(apde_plan *p, int64_t first, int64_t count, cudaStream_t st) {
@@ -682,8 +777,12 @@ void release_cached_plan() {
 
 int solve_redblack(int elem, double *grid, const double *nh, const double *nv, const double *src,
                    int64_t rows, int64_t cols, double tol, int64_t max_iter, int check_every,
-                   int temporal_depth, double *hist, int64_t *iters, double *ksec) {
+                   int temporal_depth, double *hist, int64_t *iters, double *ksec, double omega, bool kcl) {
     if (ksec) *ksec = 0.0;
+    if (!(omega > 0.0 && omega < 2.0)) {
+        set_error("solve_redblack: omega must lie in (0, 2), got %g", omega);
+        return APDE_EINVAL;
+    }
     if (max_iter <= 0) {
         *iters = max_iter;
         return APDE_OK;
@@ -736,6 +835,8 @@ int solve_redblack(int elem, double *grid, const double *nh, const double *nv, c
             else delete p;
         }
     } guard{p, use_cache};
+    p->omega = omega;
+    p->kcl = kcl;
     APDE_TRY(plan_upload(p, grid, nh, nv, src));
     const double t_uploaded = now();
     // ---- sweep loop without host round trips -------------------------------------------------------------

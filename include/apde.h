@@ -91,6 +91,24 @@ int apde_solve_redblack_multi(int dtype_bytes, double *grid, const double *noise
                               int64_t max_iter, int check_every, int temporal_depth, int n_gpus,
                               double *residual_history, int64_t *iterations_run, double *kernel_seconds);
 
+/* ------------------------------------------------------------------------------------------
+ * EXTENDED relaxation (not in the reference) -- red-black sweeps with
+ *   omega       over-relaxation, new = old + omega * (gauss_seidel_value - old), 0 < omega < 2.  For the ideal mesh the
+ *               optimum is 2 / (1 + sqrt(1 - rho^2)), rho = (cos(pi/(rows-1)) + cos(pi/(cols-1))) / 2, which cuts the
+ *               sweep count from O(N^2) to O(N).
+ *   normalised  != 0: each node divides by the sum of ITS four link conductances instead of the reference's constant 4
+ *               (solver.py:275), i.e. Kirchhoff's current law sum g_k (u_k - u) = source.  That system is diagonally
+ *               dominant at every grid size, whereas the reference's (4I - W)u = b turns indefinite -- and the
+ *               iteration diverges -- for N >~ 200 at 1 % mismatch (SURVEY finding 2).  Without links it is the same
+ *               update as the reference's.
+ * omega == 1 and normalised == 0 is apde_solve_redblack_f64/f32.  Runs on the per-colour general kernel (one pass over
+ * HBM per colour); check_every as above; residual_history / iterations_run as above.
+ * ---------------------------------------------------------------------------------------- */
+int apde_solve_redblack_ex(int dtype_bytes, double *grid, const double *noise_h, const double *noise_v,
+                           const double *source, int64_t rows, int64_t cols, double tol, int64_t max_iter,
+                           int check_every, double omega, int normalised, double *residual_history,
+                           int64_t *iterations_run, double *kernel_seconds);
+
 /* The fused depth the one-shot solves use for temporal_depth <= 0 (dtype_bytes 8 / 4, with or without mismatch). */
 int apde_default_temporal_depth(int dtype_bytes, int has_noise);
 
@@ -149,6 +167,9 @@ int apde_plan_download_array(apde_plan *plan, int which, int64_t row_lo, int64_t
 int apde_plan_fill(apde_plan *plan, const apde_fill_desc *fill);
 /* Copy this strip's owned rows into a GLOBAL host float64 grid. */
 int apde_plan_download(apde_plan *plan, double *grid);
+
+/* Select the extended update (see apde_solve_redblack_ex) for this plan's subsequent apde_plan_run calls. */
+int apde_plan_set_relaxation(apde_plan *plan, double omega, int normalised);
 
 /* Run n_sweeps red-black sweeps on `stream` (a cudaStream_t passed as void*, NULL = default),
  * fusing up to `temporal_depth` sweeps per pass.  n_sweeps must be <= the plan's temporal_depth

@@ -223,6 +223,72 @@ int64_t apde_oracle_rb_f32(float *u, const float *gh, const float *gv, const flo
     RB_BODY(float, fmaf, fabsf)
 }
 
+/* ------------------------------------------------------------------------
+ * Extended red-black relaxation (NOT in the reference -- SURVEY section 8f item 3): over-relaxation and the
+ * normalised ("KCL") conductance update, the CPU statement of rb_general_kernel (csrc/apde_redblack.cu).
+ *
+ *   plain    : t = gN*uN; t = fma(gW,uW,t); t = fma(gE,uE,t); t -= src; gs = fma(gS*0.25, uS, t*0.25)
+ *              (exactly apde_oracle_rb_*: the reference's update, divisor 4, solver.py:269-275)
+ *   kcl      : dinv = 1 / (((gN + gS) + gW) + gE);  gs = fma(gS*dinv, uS, t*dinv)
+ *              -- Kirchhoff's current law at the node, sum(g_k (u_k - u)) = src: the weighted average the
+ *              reference's docstring describes; diagonally dominant at any grid size (SURVEY finding 2)
+ *   no links : g == 1: t = (uN + uW) + uE; kcl is the same as plain (dinv = 0.25 exactly)
+ *   omega    : new = fma(omega, gs - old, old)       (omega == 1.0: new = gs, bit-identical to the plain kernels)
+ *   change = |new - old|, max over both colours, NaN ignored.
+ * ---------------------------------------------------------------------- */
+#define RBX_BODY(T, FMA, FABS)                                                             \
+    const int64_t hc = cols - 1;                                                           \
+    const int sor = (omega != (T)1);                                                       \
+    for (int64_t t = 0; t < n_sweeps; ++t) {                                               \
+        T max_change = (T)0;                                                               \
+        for (int colour = 0; colour < 2; ++colour) {                                       \
+            _Pragma("omp parallel for schedule(static) reduction(max : max_change)")       \
+            for (int64_t i = 1; i < rows - 1; ++i) {                                       \
+                int64_t j = 1 + ((i + 1 + colour) & 1);                                    \
+                for (; j < cols - 1; j += 2) {                                             \
+                    T un = u[IDX(i - 1, j)], us = u[IDX(i + 1, j)];                        \
+                    T uw = u[IDX(i, j - 1)], ue = u[IDX(i, j + 1)];                        \
+                    T tq, gsq, scale = (T)0.25;                                            \
+                    if (gh) {                                                              \
+                        T gn = gv[IDX(i - 1, j)], gs_ = gv[IDX(i, j)];                     \
+                        T gw = gh[(size_t)i * hc + (j - 1)], ge = gh[(size_t)i * hc + j];  \
+                        if (kcl) scale = (T)1 / (((gn + gs_) + gw) + ge);                  \
+                        tq = gn * un;                                                      \
+                        tq = FMA(gw, uw, tq);                                              \
+                        tq = FMA(ge, ue, tq);                                              \
+                        gsq = gs_ * scale;                                                 \
+                    } else {                                                               \
+                        tq = un + uw;                                                      \
+                        tq = tq + ue;                                                      \
+                        gsq = scale;                                                       \
+                    }                                                                      \
+                    if (src) tq = tq - src[IDX(i, j)];                                     \
+                    tq = tq * scale;                                                       \
+                    T old = u[IDX(i, j)];                                                  \
+                    T nv_ = FMA(gsq, us, tq);                                              \
+                    if (sor) nv_ = FMA(omega, nv_ - old, old);                             \
+                    T ch = FABS(nv_ - old);                                                \
+                    if (ch > max_change) max_change = ch;                                  \
+                    u[IDX(i, j)] = nv_;                                                    \
+                }                                                                          \
+            }                                                                              \
+        }                                                                                  \
+        if (hist) hist[t] = max_change;                                                    \
+    }                                                                                      \
+    return n_sweeps;
+
+int64_t apde_oracle_rbx_f64(double *u, const double *gh, const double *gv, const double *src,
+                            int64_t rows, int64_t cols, int64_t n_sweeps, double omega, int kcl, double *hist)
+{
+    RBX_BODY(double, fma, fabs)
+}
+
+int64_t apde_oracle_rbx_f32(float *u, const float *gh, const float *gv, const float *src,
+                            int64_t rows, int64_t cols, int64_t n_sweeps, float omega, int kcl, float *hist)
+{
+    RBX_BODY(float, fmaf, fabsf)
+}
+
 /* g = 1/noise in fp64 (kernel K5); the fp32 path rounds the fp64 quotient once. */
 void apde_oracle_recip_f64(const double *noise, double *g, int64_t n)
 {

@@ -45,6 +45,10 @@ def _load():
         lib.apde_oracle_rb_f64.argtypes = [_dp, _dp, _dp, _dp, _i64, _i64, _i64, _dp]
         lib.apde_oracle_rb_f32.restype = _i64
         lib.apde_oracle_rb_f32.argtypes = [_fp, _fp, _fp, _fp, _i64, _i64, _i64, _fp]
+        lib.apde_oracle_rbx_f64.restype = _i64
+        lib.apde_oracle_rbx_f64.argtypes = [_dp, _dp, _dp, _dp, _i64, _i64, _i64, ctypes.c_double, ctypes.c_int, _dp]
+        lib.apde_oracle_rbx_f32.restype = _i64
+        lib.apde_oracle_rbx_f32.argtypes = [_fp, _fp, _fp, _fp, _i64, _i64, _i64, ctypes.c_float, ctypes.c_int, _fp]
         lib.apde_oracle_recip_f64.restype = None
         lib.apde_oracle_recip_f64.argtypes = [_dp, _dp, _i64]
         lib.apde_oracle_recip_f32.restype = None
@@ -122,7 +126,7 @@ def reciprocal_links(noise: np.ndarray, dtype) -> np.ndarray:
 
 
 def red_black(grid, noise_h=None, noise_v=None, source=None, n_sweeps: int = 1,
-              dtype=np.float64, conductances=None):
+              dtype=np.float64, conductances=None, omega: float = 1.0, kcl: bool = False):
     """Red-black Gauss-Seidel, colour (i+j) even first, fixed sweep count.
 
     The CPU statement of the CUDA throughput kernels' arithmetic (expression tree
@@ -147,6 +151,17 @@ def red_black(grid, noise_h=None, noise_v=None, source=None, n_sweeps: int = 1,
     if source is not None:
         src = _chk(source, (rows, cols), np.float64, "source").astype(dtype)
     hist = np.zeros(max(int(n_sweeps), 1), dtype=dtype)
+    if omega != 1.0 or kcl:
+        # extended update (over-relaxation / normalised conductances), see RBX_BODY in apde_oracle.c
+        if dtype == np.float64:
+            lib.apde_oracle_rbx_f64(_ptr(u, _dp), _ptr(gh, _dp), _ptr(gv, _dp), _ptr(src, _dp),
+                                    rows, cols, int(n_sweeps), float(omega), int(bool(kcl)), _ptr(hist, _dp))
+        elif dtype == np.float32:
+            lib.apde_oracle_rbx_f32(_ptr(u, _fp), _ptr(gh, _fp), _ptr(gv, _fp), _ptr(src, _fp),
+                                    rows, cols, int(n_sweeps), float(np.float32(omega)), int(bool(kcl)), _ptr(hist, _fp))
+        else:
+            raise ValueError("dtype must be float32 or float64")
+        return u, hist[:n_sweeps].copy(), int(n_sweeps)
     if dtype == np.float64:
         lib.apde_oracle_rb_f64(_ptr(u, _dp), _ptr(gh, _dp), _ptr(gv, _dp), _ptr(src, _dp),
                                rows, cols, int(n_sweeps), _ptr(hist, _dp))

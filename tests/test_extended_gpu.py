@@ -1,0 +1,136 @@
+"""GPU: the extended relaxation modes (not in the reference) through the C-ABI.
+
+  redblack_sor  over-relaxed red-black Gauss-Seidel: same fixed point as the reference, O(N) sweeps;
+  redblack_kcl  each node normalised by the sum of its own link conductances: convergent at any size.
+
+Parity: at a fixed sweep count the kernel equals its CPU statement (oracle.red_black(..., omega=, kcl=)) bit for
+bit; converged, SOR agrees with the reference's lexicographic answer to 1e-10 and the normalised update with a
+sparse direct solve of Kirchhoff's equations."""
+import numpy as np
+import pytest
+
+import oracle
+from helpers import random_problem, zero_boundary, sin_source, top_hot
+from analog_pde_solver import AnalogPDESolver, DigitalSolver, _backend
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("rows,cols", [(3, 3), (5, 4), (17, 33), (64, 64), (130, 67), (257, 300)])
+@pytest.mark.parametrize("sigma,src", [(0.0, True), (0.0, False), (0.02, True), (0.01, False)])
+@pytest.mark.parametrize("mode,dt,omega,kcl", [
+    ("redblack_sor", np.float64, 1.7, False), ("redblack_sor32", np.float32, 1.5, False),
+    ("redblack_kcl", np.float64, None, True), ("redblack_kcl32", np.float32, None, True),
+    ("redblack_kcl", np.float64, 1.85, True), ("redblack_sor", np.float64, 0.8, False)])
+def test_extended_update_bit_exact_vs_oracle(rows, cols, sigma, src, mode, dt, omega, kcl):
+    k = 11
+    g0, nh, nv, s = random_problem(rows, cols, sigma, seed=rows * 17 + cols, with_source=src)
+    ru, rh, _ = oracle.red_black(g0, nh, nv, s, k, dtype=dt, omega=1.0 if omega is None else omega, kcl=kcl)
+    g = g0.copy()
+    hist, n, _ = _backend.solve(mode, g, nh, nv, s, 0.0, k, check_every=4, omega=omega)
+    assert n == k
+    assert hist.astype(dt).tobytes() == rh.tobytes()
+    assert g.astype(dt).tobytes() == ru.tobytes()
+
+
+def test_sor_default_omega_is_the_optimum_and_reaches_the_reference_answer_fast():
+    """64 x 64 Poisson (BASELINE config 2 size): the reference needs 4070 sweeps to 1e-7; optimal SOR needs a
+    few hundred to 1e-13 and lands within 1e-10 of the reference's converged (tol 1e-13) lexicographic answer."""
+    n = 64
+    d = DigitalSolver(rows=n, cols=n)
+    u = d.solve(zero_boundary, source_fn=sin_source, tol=1e-13, max_iter=100_000, mode="redblack_sor")
+    assert d.iterations_run < 400
+    assert abs(_backend.optimal_omega(n, n) - 2.0 / (1.0 + np.sin(np.pi / (n - 1)))) < 1e-14
+    g0 = np.zeros((n, n))
+    src = np.array([[sin_source(i, j, n, n) for j in range(n)] for i in range(n)]) / (n - 1) ** 2
+    ref, _, it = oracle.gauss_seidel(g0, None, None, src, 1e-13, 200_000)
+    assert it > 10 * d.iterations_run
+    assert np.max(np.abs(u - ref)) <= 1e-10 * np.max(np.abs(ref))
+    # the same through the analog class with mismatch on a grid where (4I - W) is still definite
+    a = AnalogPDESolver(rows=48, cols=48, noise_level=0.01, rng_seed=0)
+    ua = a.solve(top_hot, tol=1e-13, max_iter=100_000, mode="redblack_sor", omega=1.8)
+    g0 = np.zeros((48, 48))
+    g0[0, :] = 1.0
+    ref, _, it = oracle.gauss_seidel(g0, a._noise_h, a._noise_v, None, 1e-13, 400_000)
+    assert a.iterations_run * 5 < it and np.max(np.abs(ua - ref)) <= 1e-10
+
+
+def test_normalised_update_converges_where_the_reference_update_diverges():
+    """N = 512, 1 % mismatch (seed 0): lambda_max(W) > 4, so the reference's divide-by-4 iteration grows without
+    bound (SURVEY finding 2) -- its red-black form does too.  The normalised update converges, and its fixed point
+    solves Kirchhoff's equations  sum_k g_k (u - u_k) = -src  (checked against a sparse direct solve)."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    n = 512
+    a = AnalogPDESolver(rows=n, cols=n, noise_level=0.01, rng_seed=0)
+    g0 = np.zeros((n, n))
+    g0[0, :] = 1.0
+    # the reference's update: still moving (and growing) after 30 000 sweeps
+    g = g0.copy()
+    hist, it, _ = _backend.solve("redblack", g, a._noise_h, a._noise_v, None, 1e-9, 30_000, check_every=500)
+    assert it == 30_000 and hist[-1] > hist[5000] > 0
+    # normalised + over-relaxed: converges
+    u = a.solve(top_hot, tol=1e-12, max_iter=20_000, mode="redblack_kcl", omega=_backend.optimal_omega(n, n))
+    assert a.iterations_run < 20_000 and a.residual_history[-1] < 1e-12
+    # Kirchhoff: (sum g) u - sum g_k u_k = 0 at interior nodes, Dirichlet ring from g0
+    gh, gv = 1.0 / a._noise_h, 1.0 / a._noise_v
+    idx = -np.ones((n, n), dtype=np.int64)
+    idx[1:-1, 1:-1] = np.arange((n - 2) * (n - 2)).reshape(n - 2, n - 2)
+    ii, jj = np.meshgrid(np.arange(1, n - 1), np.arange(1, n - 1), indexing="ij")
+    ii, jj = ii.ravel(), jj.ravel()
+    me = idx[ii, jj]
+    links = [(ii - 1, jj, gv[ii - 1, jj]), (ii + 1, jj, gv[ii, jj]), (ii, jj - 1, gh[ii, jj - 1]), (ii, jj + 1, gh[ii, jj])]
+    diag = sum(l[2] for l in links)
+    rows_, cols_, vals, rhs = [me], [me], [diag], np.zeros(me.size)
+    for (pi, pj, gk) in links:
+        nb = idx[pi, pj]
+        inner = nb >= 0
+        rows_.append(me[inner]); cols_.append(nb[inner]); vals.append(-gk[inner])
+        np.add.at(rhs, me[~inner], gk[~inner] * g0[pi[~inner], pj[~inner]])
+    A = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows_), np.concatenate(cols_))), shape=(me.size, me.size))
+    x = spla.spsolve(A.tocsc(), rhs)
+    assert np.max(np.abs(u[1:-1, 1:-1].ravel() - x)) <= 1e-9
+
+
+def test_modes_validate_their_arguments():
+    d = DigitalSolver(rows=12, cols=12)
+    with pytest.raises(ValueError):
+        d.solve(top_hot, mode="redblack_sor", omega=2.5)
+    with pytest.raises(ValueError):
+        d.solve(top_hot, mode="no_such_mode")
+    u1 = d.solve(top_hot, tol=1e-9, mode="redblack_kcl")       # ideal links: the reference's own update
+    u2 = DigitalSolver(rows=12, cols=12).solve(top_hot, tol=1e-9, mode="redblack")
+    assert u1.tobytes() == u2.tobytes()
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_extended_update_on_two_strips_equals_one_strip(dt):
+    """apde_plan_set_relaxation on row strips with a halo exchange every `depth` sweeps == the single strip, bitwise."""
+    rows, cols, depth, groups = 150, 90, 2, 5
+    g0, nh, nv, s = random_problem(rows, cols, 0.01, seed=9)
+    lib = _backend.load()
+    kw = dict(dtype=dt, has_noise=True, has_source=True, temporal_depth=depth)
+    with _backend.Plan(rows, cols, **kw) as whole:
+        whole.set_relaxation(1.6, True)
+        whole.upload(g0, nh, nv, s)
+        for g in range(groups):
+            whole.run(depth, g * depth)
+        ref, ref_hist = whole.download(), whole.residuals(0, groups * depth)
+    a, b = _backend.Plan(rows, cols, 0, 70, **kw), _backend.Plan(rows, cols, 70, rows, **kw)
+    for p in (a, b):
+        p.set_relaxation(1.6, True)
+        p.upload(g0, nh, nv, s)
+    for g in range(groups):
+        a.run(depth, g * depth)
+        b.run(depth, g * depth)
+        sa, ra, nb = a.halo(1)
+        sb, rb, _ = b.halo(0)
+        _backend.check(lib.apde_memcpy_dtod(rb, sa, nb, None))
+        _backend.check(lib.apde_memcpy_dtod(ra, sb, nb, None))
+    out = np.zeros((rows, cols))
+    a.download(out)
+    b.download(out)
+    hist = np.maximum(a.residuals(0, groups * depth), b.residuals(0, groups * depth))
+    a.close()
+    b.close()
+    assert out.tobytes() == ref.tobytes() and hist.tobytes() == ref_hist.tobytes()
