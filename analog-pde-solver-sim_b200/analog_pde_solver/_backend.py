@@ -30,6 +30,7 @@ EXPORTED_SYMBOLS = (
     "apde_plan_create", "apde_plan_destroy", "apde_plan_upload", "apde_plan_upload_rows", "apde_plan_download_rows", "apde_plan_fill",
     "apde_plan_download", "apde_plan_clear_residuals", "apde_plan_run", "apde_plan_halo", "apde_plan_residuals",
     "apde_plan_read_residuals", "apde_plan_launch_count", "apde_plan_checksum", "apde_plan_checksum_bits", "apde_memcpy_dtod", "apde_selftest_division", "apde_plan_energy_sums", "apde_plan_download_array", "apde_default_temporal_depth", "apde_solve_redblack_ex", "apde_plan_set_relaxation",
+    "apde_solve_multigrid", "apde_multigrid_levels",
 )
 
 
@@ -93,6 +94,11 @@ def load():
     lib.apde_solve_redblack_ex.restype = ctypes.c_int
     lib.apde_solve_redblack_ex.argtypes = [ctypes.c_int, _dp, _dp, _dp, _dp] + solve_tail + [
         ctypes.c_int, ctypes.c_double, ctypes.c_int, _dp, _i64p, _dp]
+    lib.apde_solve_multigrid.restype = ctypes.c_int
+    lib.apde_solve_multigrid.argtypes = [ctypes.c_int, _dp, _dp, _i64, _i64, ctypes.c_double, _i64, ctypes.c_int,
+                                         ctypes.c_int, ctypes.c_int, _dp, _i64p, _dp]
+    lib.apde_multigrid_levels.restype = ctypes.c_int
+    lib.apde_multigrid_levels.argtypes = [_i64, _i64]
     lib.apde_plan_set_relaxation.restype = ctypes.c_int
     lib.apde_plan_set_relaxation.argtypes = [_vp, ctypes.c_double, ctypes.c_int]
     lib.apde_default_temporal_depth.restype = ctypes.c_int
@@ -134,6 +140,11 @@ def default_temporal_depth(dtype: str, has_noise: bool) -> int:
     return int(load().apde_default_temporal_depth(8 if dtype in ("f64", "float64") else 4, int(bool(has_noise))))
 
 
+def multigrid_levels(rows: int, cols: int) -> int:
+    """Number of grid levels a V-cycle gets on a rows x cols grid (1 = the shape does not coarsen)."""
+    return int(load().apde_multigrid_levels(int(rows), int(cols)))
+
+
 def check(rc: int) -> None:
     if rc != APDE_OK:
         msg = load().apde_last_error()
@@ -155,7 +166,7 @@ def _as_f64(a, shape, name):
 
 EXACT_PATHS = {"auto": 0, "small": 1, "ring": 2}
 MODES = ("exact", "redblack", "redblack64", "redblack32",
-         "redblack_sor", "redblack_sor32", "redblack_kcl", "redblack_kcl32")
+         "redblack_sor", "redblack_sor32", "redblack_kcl", "redblack_kcl32", "multigrid", "multigrid32")
 EXTENDED_MODES = {  # mode -> (dtype bytes, normalised conductances, over-relaxed by default)
     "redblack_sor": (8, False, True), "redblack_sor32": (4, False, True),
     "redblack_kcl": (8, True, False), "redblack_kcl32": (4, True, False),
@@ -188,6 +199,13 @@ def _solve_once(lib, mode, grid, nh, nv, src, tol, max_iter, check_every, tempor
     if mode == "exact":
         rc = lib.apde_solve_exact_f64_path(*head, _ptr(hist), ctypes.byref(iters), ctypes.byref(ksec),
                                            EXACT_PATHS[exact_path])
+    elif mode in ("multigrid", "multigrid32"):
+        if nh is not None or nv is not None:
+            raise ValueError("multigrid supports the ideal mesh only (no link mismatch); use redblack_kcl / redblack_sor")
+        nu = int(os.environ.get("APDE_MG_SMOOTH", "0"))
+        rc = lib.apde_solve_multigrid(4 if mode == "multigrid32" else 8, _ptr(grid), _ptr(src), rows, cols, float(tol),
+                                      max_iter, nu, nu, int(os.environ.get("APDE_MG_COARSE_SWEEPS", "0")), _ptr(hist),
+                                      ctypes.byref(iters), ctypes.byref(ksec))
     elif mode in EXTENDED_MODES:
         elem, kcl, sor = EXTENDED_MODES[mode]
         if omega is None:

@@ -1,0 +1,248 @@
+// apde_multigrid.cu -- geometric multigrid V-cycle for the ideal mesh (no link mismatch), with the fused red-black
+// kernels as the smoother (not in the reference).
+//
+// The reference relaxes  4 u_ij - (u_N + u_S + u_W + u_E) = -src_ij  by Gauss-Seidel (solver.py:350-356), which needs
+// O(N^2) sweeps on an N x N grid.  A V(nu1, nu2) cycle reduces the error by a constant factor per cycle at the cost of
+// ~ (nu1 + nu2) * 4/3 fine-grid sweeps, independent of N:
+//     smooth nu1 sweeps (red-black, fused kernel)  ->  residual r = -src - 4u + sum(neighbours)
+//     -> restrict to the next coarser grid (full weighting transposed, src_c = -P^T r; rediscretised 5-point operator)
+//     -> recurse with a zero initial error -> prolong the coarse error bilinearly and add it -> smooth nu2 sweeps.
+// Vertex-centred coarsening: a level of (r, c) nodes coarsens to ((r-1)/2+1, (c-1)/2+1) while both r-1 and c-1 are
+// even and the coarse grid keeps at least 3 nodes per direction; the coarsest level is relaxed by a fixed number of
+// sweeps.  Grids of 2^k+1 nodes per side coarsen all the way down; a side like 4096 (r-1 odd) does not coarsen at
+// all, and the solve is refused (use redblack_sor there).
+//
+// Every level is an ordinary apde_plan (padded strip layout, plan dtype), so the smoother is literally
+// plan_run(); the two transfer kernels below work between plans.  All arithmetic is explicit round-to-nearest with a
+// fixed association, restated by the CPU checker of the tests, so cycles are bit-reproducible.
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "apde_plan.h"
+#include "apde_rb_common.cuh"
+
+namespace apde {
+
+// r_ij = ((((uN + uS) + uW) + uE) - 4 u) - src   at interior nodes, 0 on the ring
+template <typename T>
+__device__ __forceinline__ T mg_residual(const T *__restrict__ u, const T *__restrict__ src, long long c, long long pitch) {
+    T t = Ar<T>::add(u[c - pitch], u[c + pitch]);
+    t = Ar<T>::add(t, u[c - 1]);
+    t = Ar<T>::add(t, u[c + 1]);
+    t = Ar<T>::sub(t, Ar<T>::mul((T)4, u[c]));
+    if (src) t = Ar<T>::sub(t, src[c]);
+    return t;
+}
+
+// coarse source: src_c(I,J) = -( 0.5*rowsum(2I-1) + rowsum(2I) + 0.5*rowsum(2I+1) ),
+// rowsum(i) = (0.5*r(i,2J-1) + r(i,2J)) + 0.5*r(i,2J+1); coarse u = 0 everywhere (zero initial error, zero ring)
+template <typename T>
+__global__ void mg_restrict_kernel(const T *__restrict__ uf, const T *__restrict__ sf, long long pitch_f, long long padl_f,
+                                   int rows_f, int cols_f, T *__restrict__ uc0, T *__restrict__ uc1, T *__restrict__ sc,
+                                   long long pitch_c, long long padl_c, int rows_c, int cols_c) {
+    const long long n = (long long)rows_c * cols_c;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        const int I = (int)(k / cols_c), J = (int)(k - (long long)I * cols_c);
+        const long long cc = (long long)I * pitch_c + padl_c + J;
+        uc0[cc] = (T)0;
+        uc1[cc] = (T)0;
+        T out = (T)0;
+        if (I > 0 && I < rows_c - 1 && J > 0 && J < cols_c - 1) {
+            T rs[3];
+#pragma unroll
+            for (int d = -1; d <= 1; ++d) {
+                const int i = 2 * I + d;
+                T r3[3];
+#pragma unroll
+                for (int e = -1; e <= 1; ++e) {
+                    const int j = 2 * J + e;
+                    const bool interior = i > 0 && i < rows_f - 1 && j > 0 && j < cols_f - 1;
+                    r3[e + 1] = interior ? mg_residual<T>(uf, sf, (long long)i * pitch_f + padl_f + j, pitch_f) : (T)0;
+                }
+                rs[d + 1] = Ar<T>::add(Ar<T>::add(Ar<T>::mul((T)0.5, r3[0]), r3[1]), Ar<T>::mul((T)0.5, r3[2]));
+            }
+            const T b = Ar<T>::add(Ar<T>::add(Ar<T>::mul((T)0.5, rs[0]), rs[1]), Ar<T>::mul((T)0.5, rs[2]));
+            out = -b;
+        }
+        sc[cc] = out;
+    }
+}
+
+// fine u += P e  (bilinear): even/even copy, one odd index the mean of two, both odd 0.25*(((e00+e01)+e10)+e11)
+// corr_max (optional): max |P e| over the interior, max-accumulated on the bit pattern (for the stop criterion)
+template <typename T>
+__global__ void mg_prolong_kernel(T *__restrict__ uf, long long pitch_f, long long padl_f, int rows_f, int cols_f,
+                                  const T *__restrict__ ec, long long pitch_c, long long padl_c, T *corr_max) {
+    const long long n = (long long)(rows_f - 2) * (cols_f - 2);
+    T mx = (T)0;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        const int i = 1 + (int)(k / (cols_f - 2)), j = 1 + (int)(k - (long long)(i - 1) * (cols_f - 2));
+        const int I = i >> 1, J = j >> 1;
+        const T *e = ec + (long long)I * pitch_c + padl_c + J;
+        T corr;
+        if (!(i & 1) && !(j & 1)) corr = e[0];
+        else if (!(i & 1)) corr = Ar<T>::mul((T)0.5, Ar<T>::add(e[0], e[1]));
+        else if (!(j & 1)) corr = Ar<T>::mul((T)0.5, Ar<T>::add(e[0], e[pitch_c]));
+        else corr = Ar<T>::mul((T)0.25, Ar<T>::add(Ar<T>::add(Ar<T>::add(e[0], e[1]), e[pitch_c]), e[pitch_c + 1]));
+        const long long c = (long long)i * pitch_f + padl_f + j;
+        uf[c] = Ar<T>::add(uf[c], corr);
+        mx = max_ignore_nan(mx, Ar<T>::abs(corr));
+    }
+    if (corr_max) {
+        mx = warp_max(mx);
+        if ((threadIdx.x & 31) == 0 && mx > (T)0) atomic_max_nonneg(corr_max, mx);
+    }
+}
+
+namespace {
+
+struct Level {
+    apde_plan *plan = nullptr;
+    int rows = 0, cols = 0;
+    ~Level() { delete plan; }
+};
+
+template <typename T>
+int restrict_to(apde_plan *f, apde_plan *c) {
+    const int tg = f->sm_count * 8;
+    mg_restrict_kernel<T><<<tg, 256>>>(f->U<T>(f->cur), f->S<T>(), f->pitch, f->padl, (int)f->d.grows, (int)f->d.cols,
+                                       c->U<T>(0), c->U<T>(1), c->S<T>(), c->pitch, c->padl, (int)c->d.grows, (int)c->d.cols);
+    APDE_CUDA(cudaGetLastError());
+    c->cur = 0;
+    c->pass_open = false;
+    c->filled = true;
+    f->launches++;
+    return APDE_OK;
+}
+template <typename T>
+int prolong_from(apde_plan *f, apde_plan *c, bool want_max) {
+    const int tg = f->sm_count * 8;
+    T *corr_max = nullptr;
+    if (want_max) {  // scratch bytes 40..47 (0..23 checksums, 32..35 the stop flag)
+        corr_max = reinterpret_cast<T *>(static_cast<char *>(f->scratch.p) + 40);
+        APDE_CUDA(cudaMemsetAsync(corr_max, 0, sizeof(T), 0));
+    }
+    mg_prolong_kernel<T><<<tg, 256>>>(f->U<T>(f->cur), f->pitch, f->padl, (int)f->d.grows, (int)f->d.cols,
+                                      c->U<T>(c->cur), c->pitch, c->padl, corr_max);
+    APDE_CUDA(cudaGetLastError());
+    f->launches++;
+    return APDE_OK;
+}
+
+}  // namespace
+
+int mg_level_count(int64_t rows, int64_t cols) {
+    int n = 1;
+    while ((rows - 1) % 2 == 0 && (cols - 1) % 2 == 0 && (rows - 1) / 2 + 1 >= 3 && (cols - 1) / 2 + 1 >= 3) {
+        rows = (rows - 1) / 2 + 1;
+        cols = (cols - 1) / 2 + 1;
+        ++n;
+    }
+    return n;
+}
+
+// V-cycles until a whole cycle moves no node by tol or more (the reference's criterion, solver.py:283, applied per
+// cycle instead of per sweep -- a single smoothing sweep barely moves a smooth error on a fine grid, so its
+// max_change says little about convergence), or max_cycles.  hist[c] = an upper bound of cycle c's max change:
+// the sum of its fine-grid smoothing sweeps' max_change values and of max |coarse-grid correction|, accumulated in
+// fp64 in the order pre-smoothing sweeps, correction, post-smoothing sweeps.  *cycles = cycles run.
+int solve_multigrid(int elem, double *grid, const double *src, int64_t rows, int64_t cols, double tol,
+                    int64_t max_cycles, int nu1, int nu2, int coarse_sweeps, double *hist, int64_t *cycles, double *ksec) {
+    if (ksec) *ksec = 0.0;
+    if (max_cycles <= 0) {
+        *cycles = max_cycles;
+        return APDE_OK;
+    }
+    if (rows < 3 || cols < 3) {
+        const int64_t n = (0.0 < tol) ? 1 : max_cycles;
+        for (int64_t k = 0; k < n; ++k) hist[k] = 0.0;
+        *cycles = n;
+        return APDE_OK;
+    }
+    if (nu1 <= 0) nu1 = 2;
+    if (nu2 <= 0) nu2 = 2;
+    if (coarse_sweeps <= 0) coarse_sweeps = 32;
+    const int n_levels = mg_level_count(rows, cols);
+    if (n_levels < 2 && std::max(rows, cols) > 9) {
+        set_error("multigrid: a %lld x %lld grid does not coarsen (rows-1 and cols-1 must be even; 2^k+1 nodes per side "
+                  "coarsen fully) -- use the redblack_sor mode for this size",
+                  (long long)rows, (long long)cols);
+        return APDE_EINVAL;
+    }
+    release_cached_plan();
+    std::vector<std::unique_ptr<Level>> lv;
+    int64_t r = rows, c = cols;
+    for (int l = 0; l < n_levels; ++l) {
+        auto L = std::make_unique<Level>();
+        apde_plan_desc d{};
+        d.dtype_bytes = elem;
+        d.has_noise = 0;
+        d.has_source = (l > 0 || src != nullptr) ? 1 : 0;
+        d.temporal_depth = std::min(std::max(nu1, nu2), max_temporal_depth());
+        d.grows = r;
+        d.cols = c;
+        d.row_begin = 0;
+        d.row_end = r;
+        APDE_TRY(plan_create(&L->plan, &d));
+        L->rows = (int)r;
+        L->cols = (int)c;
+        lv.push_back(std::move(L));
+        r = (r - 1) / 2 + 1;
+        c = (c - 1) / 2 + 1;
+    }
+    apde_plan *fine = lv[0]->plan;
+    APDE_TRY(plan_upload(fine, grid, nullptr, nullptr, src));
+    EventPair ev;
+    APDE_TRY(ev.init());
+    APDE_CUDA(cudaEventRecord(ev.a));
+    auto smooth = [&](apde_plan *p, int n, int base) { return plan_run(p, n, base, 0, 0); };
+    auto down = [&](apde_plan *f, apde_plan *cz) { return elem == 8 ? restrict_to<double>(f, cz) : restrict_to<float>(f, cz); };
+    auto up = [&](apde_plan *f, apde_plan *cz, bool mx) {
+        return elem == 8 ? prolong_from<double>(f, cz, mx) : prolong_from<float>(f, cz, mx);
+    };
+    std::vector<double> sw((size_t)(nu1 + nu2));
+    int64_t done = 0;
+    bool stop = false;
+    while (done < max_cycles && !stop) {
+        for (int l = 0; l + 1 < n_levels; ++l) {
+            APDE_TRY(smooth(lv[l]->plan, nu1, 0));
+            APDE_TRY(down(lv[l]->plan, lv[l + 1]->plan));
+        }
+        APDE_TRY(smooth(lv[n_levels - 1]->plan, n_levels > 1 ? coarse_sweeps : nu1 + nu2, 0));
+        for (int l = n_levels - 2; l >= 0; --l) {
+            APDE_TRY(up(lv[l]->plan, lv[l + 1]->plan, l == 0));
+            APDE_TRY(smooth(lv[l]->plan, nu2, nu1));  // slots nu1.. : the pre-smoothing values of this cycle stay readable
+        }
+        // how far did this cycle move the fine grid, at most?
+        APDE_TRY(plan_read_residuals(fine, 0, nu1 + nu2, sw.data(), 0));
+        double corr = 0.0;
+        if (n_levels > 1) {
+            char raw[8] = {0};
+            APDE_CUDA(cudaMemcpy(raw, static_cast<char *>(fine->scratch.p) + 40, (size_t)elem, cudaMemcpyDeviceToHost));
+            if (elem == 8) memcpy(&corr, raw, 8);
+            else {
+                float f32 = 0.f;
+                memcpy(&f32, raw, 4);
+                corr = (double)f32;
+            }
+        }
+        double moved = 0.0;
+        for (int k = 0; k < nu1; ++k) moved += sw[(size_t)k];
+        moved += corr;
+        for (int k = 0; k < nu2; ++k) moved += sw[(size_t)(nu1 + k)];
+        hist[done] = moved;
+        if (moved < tol) stop = true;
+        ++done;
+    }
+    APDE_CUDA(cudaEventRecord(ev.b));
+    APDE_CUDA(cudaEventSynchronize(ev.b));
+    float ms = 0.f;
+    APDE_CUDA(cudaEventElapsedTime(&ms, ev.a, ev.b));
+    if (ksec) *ksec = ms * 1e-3;
+    *cycles = done;
+    return plan_download(fine, grid);
+}
+
+}  // namespace apde

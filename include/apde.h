@@ -109,6 +109,24 @@ int apde_solve_redblack_ex(int dtype_bytes, double *grid, const double *noise_h,
                            int check_every, double omega, int normalised, double *residual_history,
                            int64_t *iterations_run, double *kernel_seconds);
 
+/* ------------------------------------------------------------------------------------------
+ * MULTIGRID (not in the reference) -- geometric V(nu1, nu2) cycles for the ideal mesh
+ * (no link mismatch: DigitalSolver, or AnalogPDESolver with noise_level 0), the fused red-black kernels as smoother,
+ * full-weighting restriction, bilinear prolongation, rediscretised 5-point operator on every level.  Vertex-centred
+ * coarsening: a level coarsens while rows-1 and cols-1 are even (2^k+1 nodes per side coarsen fully);
+ * apde_multigrid_levels() says how many levels a shape gets, and a shape that does not coarsen at all is refused with
+ * APDE_EINVAL (use apde_solve_redblack_ex with omega there).
+ * A cycle costs about (nu1 + nu2) * 4/3 fine-grid sweeps and reduces the error by a factor independent of the grid
+ * size.  residual_history[c] bounds how far cycle c moved any node: the sum of its fine-grid smoothing sweeps' max_change
+ * and of max |coarse-grid correction|; the solve stops after the first cycle where that is < tol (the reference's
+ * criterion, solver.py:283, applied to a whole cycle -- one smoothing sweep barely moves a smooth error on a fine grid,
+ * so a per-sweep test would stop far too early) or after max_cycles; *cycles_run is the number of cycles.  nu1 / nu2 / coarse_sweeps <= 0 select 2 / 2 / 32.
+ * ---------------------------------------------------------------------------------------- */
+int apde_solve_multigrid(int dtype_bytes, double *grid, const double *source, int64_t rows, int64_t cols, double tol,
+                         int64_t max_cycles, int nu1, int nu2, int coarse_sweeps, double *residual_history,
+                         int64_t *cycles_run, double *kernel_seconds);
+int apde_multigrid_levels(int64_t rows, int64_t cols);
+
 /* The fused depth the one-shot solves use for temporal_depth <= 0 (dtype_bytes 8 / 4, with or without mismatch). */
 int apde_default_temporal_depth(int dtype_bytes, int has_noise);
 

@@ -173,4 +173,95 @@ def red_black(grid, noise_h=None, noise_v=None, source=None, n_sweeps: int = 1,
     return u, hist[:n_sweeps].copy(), int(n_sweeps)
 
 
-__all__ = ["build", "gauss_seidel", "gauss_seidel_mt", "red_black", "reciprocal_links", "max_threads"]
+def _mg_levels(rows, cols):
+    n = 1
+    while (rows - 1) % 2 == 0 and (cols - 1) % 2 == 0 and (rows - 1) // 2 + 1 >= 3 and (cols - 1) // 2 + 1 >= 3:
+        rows, cols = (rows - 1) // 2 + 1, (cols - 1) // 2 + 1
+        n += 1
+    return n
+
+
+def multigrid(grid, source=None, tol: float = 1e-8, max_cycles: int = 50, nu1: int = 2, nu2: int = 2,
+              coarse_sweeps: int = 32, dtype=np.float64):
+    """CPU statement of csrc/apde_multigrid.cu (NOT in the reference): V(nu1, nu2) cycles on the ideal mesh,
+    red-black smoothing (red_black above), r = ((((uN+uS)+uW)+uE) - 4u) - src, coarse source
+    -((0.5*rs(2I-1) + rs(2I)) + 0.5*rs(2I+1)) with rs(i) = (0.5*r(i,2J-1) + r(i,2J)) + 0.5*r(i,2J+1), bilinear
+    prolongation 0.5*(a+b) / 0.25*(((a+b)+c)+d); same association everywhere, so results match the GPU bit for bit.
+    Per cycle the history holds an upper bound of how far the cycle moved any fine node: the fp64 sum, in order, of the
+    pre-smoothing sweeps' max_change, max |coarse-grid correction| and the post-smoothing sweeps' max_change.
+    Returns (grid in dtype, that history, cycles)."""
+    dt = np.dtype(dtype).type
+    u = np.array(grid, dtype=np.float64).astype(dtype)
+    rows, cols = u.shape
+    src = None if source is None else np.asarray(source, dtype=np.float64).astype(dtype)
+    L = _mg_levels(rows, cols)
+    half, quarter, four = dt(0.5), dt(0.25), dt(4)
+
+    def smooth(uu, ss, n):
+        out, h, _ = red_black(uu.astype(np.float64), None, None, None if ss is None else ss.astype(np.float64), n, dtype=dtype)
+        return out, h
+
+    def restrict(uu, ss):
+        r = np.zeros_like(uu)
+        t = (uu[:-2, 1:-1] + uu[2:, 1:-1])
+        t = t + uu[1:-1, :-2]
+        t = t + uu[1:-1, 2:]
+        t = t - four * uu[1:-1, 1:-1]
+        if ss is not None:
+            t = t - ss[1:-1, 1:-1]
+        r[1:-1, 1:-1] = t
+        rc, cc = (uu.shape[0] - 1) // 2 + 1, (uu.shape[1] - 1) // 2 + 1
+        rs = (half * r[:, 1:-2:2] + r[:, 2:-1:2]) + half * r[:, 3::2]          # columns J = 1 .. cc-2
+        b = (half * rs[1:-2:2] + rs[2:-1:2]) + half * rs[3::2]                  # rows    I = 1 .. rc-2
+        sc = np.zeros((rc, cc), dtype=dtype)
+        sc[1:-1, 1:-1] = -b
+        return sc
+
+    def prolong(uu, e, stats=None):
+        corr = np.zeros_like(uu)
+        corr[::2, ::2] = e
+        corr[::2, 1::2] = half * (e[:, :-1] + e[:, 1:])
+        corr[1::2, ::2] = half * (e[:-1, :] + e[1:, :])
+        corr[1::2, 1::2] = quarter * (((e[:-1, :-1] + e[:-1, 1:]) + e[1:, :-1]) + e[1:, 1:])
+        out = uu.copy()
+        out[1:-1, 1:-1] = uu[1:-1, 1:-1] + corr[1:-1, 1:-1]
+        if stats is not None:
+            a = np.abs(corr[1:-1, 1:-1])
+            a = a[~np.isnan(a)]
+            stats.append(float(a.max()) if a.size else 0.0)
+        return out
+
+    hist = []
+    for _ in range(int(max_cycles)):
+        us, ss = [u], [src]
+        pre = post = np.zeros(0)
+        corr = []
+        for l in range(L - 1):
+            us[l], h = smooth(us[l], ss[l], nu1)
+            if l == 0:
+                pre = h
+            sc = restrict(us[l], ss[l])
+            us.append(np.zeros_like(sc))
+            ss.append(sc)
+        us[L - 1], h = smooth(us[L - 1], ss[L - 1], coarse_sweeps if L > 1 else nu1 + nu2)
+        if L == 1:
+            pre, post = h[:nu1], h[nu1:]
+        for l in range(L - 2, -1, -1):
+            us[l] = prolong(us[l], us[l + 1], corr if l == 0 else None)
+            us[l], h = smooth(us[l], ss[l], nu2)
+            if l == 0:
+                post = h
+        u = us[0]
+        moved = 0.0
+        for v in pre:
+            moved += float(v)
+        moved += corr[0] if corr else 0.0
+        for v in post:
+            moved += float(v)
+        hist.append(moved)
+        if moved < tol:
+            break
+    return u, np.array(hist, dtype=np.float64), len(hist)
+
+
+__all__ = ["build", "gauss_seidel", "gauss_seidel_mt", "red_black", "reciprocal_links", "max_threads", "multigrid"]

@@ -12,5 +12,5 @@ done
 wait
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../lib/libapde_$NAME.so build/apde_exact.o build/apde_redblack.o \
   build/var_$NAME/apde_rb_stream_f64.o build/var_$NAME/apde_rb_stream_f32.o build/var_$NAME/apde_rb_pipe_f64.o build/var_$NAME/apde_rb_pipe_f32.o \
-  build/apde_api.o -Xcompiler -fPIC
+  build/apde_multigrid.o build/apde_api.o -Xcompiler -fPIC
 echo built $NAME
