@@ -445,8 +445,38 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
     }
 }
 
+// What the launcher needs to cut the owned rows into row blocks (the block height is chosen per kernel
+// instantiation, because it depends on how many warps of that instantiation are resident).
+struct BlockReq {
+    long long owned, halo;
+    bool top_nb, bot_nb;
+    int phase;
+    long long forced_rbh;  // > 0: APDE_ROW_BLOCK
+};
+
+// Row-block height.  One launch runs n_blocks * n_strips work items on W resident warps in ceil(items / W) rounds of
+// (rbh + 2*NS + start-up) row iterations each; taller blocks recompute fewer halo rows (2*NS per block) but the
+// last round must not run half empty.  Pick the height with the lowest modelled time (measured on B200, 16384^2
+// fp64 depth 3: 256 rows 469 GLUP/s, 1024 rows 500 GLUP/s; fp32, 12 warps per SM: 1024 rows 892, 256 rows 1003).
+inline long long pick_row_block(long long owned, long long n_strips, long long warps, int ns, long long halo) {
+    long long best = std::max<long long>(256, halo);
+    double best_cost = 1e300;
+    const long long nb_lo = std::max<long long>(1, (owned + 4095) / 4096), nb_hi = std::max<long long>(nb_lo, std::min<long long>(owned / 64, 512));
+    for (long long nb = nb_lo; nb <= nb_hi; ++nb) {
+        const long long rbh = std::max<long long>((owned + nb - 1) / nb, std::max<long long>(halo, 8));
+        const long long blocks = (owned + rbh - 1) / rbh;
+        const long long rounds = (blocks * n_strips + warps - 1) / warps;
+        const double cost = (double)rounds * (double)(rbh + 2 * ns + 12);
+        if (cost < best_cost * 0.999) {
+            best_cost = cost;
+            best = rbh;
+        }
+    }
+    return best;
+}
+
 template <int C, int TD, bool NOISE, bool SRC>
-int launch_pass(apde_plan *p, const StreamArgs &a, cudaStream_t st) {
+int launch_pass(apde_plan *p, StreamArgs &a, const BlockReq &rq, cudaStream_t st) {
 #ifdef RBS_TMA
     constexpr size_t smem = (size_t)(RBS_THREADS / 32) * (RBS_TMA_SLOTS * 32 * C * sizeof(T) + 8 * RBS_TMA_SLOTS);
 #else
@@ -461,6 +491,27 @@ int launch_pass(apde_plan *p, const StreamArgs &a, cudaStream_t st) {
         blocks_per_sm = n > 0 ? n : 1;
     }
     const long long warps_per_block = RBS_THREADS / 32;
+    const long long resident_warps = (long long)p->sm_count * blocks_per_sm * warps_per_block;
+    // ---- row blocks (the same partition in every phase of a pass) ------------------------------------------
+    a.rbh = rq.forced_rbh > 0 ? std::max(rq.forced_rbh, rq.halo)  // an edge block must hold the rows the halo exchange sends
+                              : pick_row_block(rq.owned, a.n_strips, resident_warps, 2 * TD, rq.halo);
+    const long long nblk = (rq.owned + a.rbh - 1) / a.rbh;
+    // edge blocks: the leading / trailing row blocks that together hold the `halo` outermost owned
+    // rows on a side with a neighbour strip (those rows are what the halo exchange ships right after
+    // phase 1).  Blocks are rbh >= halo rows, except the last one, which holds the remainder: when
+    // that is shorter than the halo the block before it is an edge block too.
+    const long long last_rows = rq.owned - (nblk - 1) * a.rbh;
+    long long ea = (rq.top_nb ? 1 : 0), eb = (rq.bot_nb ? (last_rows < rq.halo ? 2 : 1) : 0);
+    if (ea + eb > nblk) { ea = std::min<long long>(ea, nblk); eb = nblk - ea; }
+    if (rq.phase == 0) {
+        a.blk_a0 = 0; a.blk_an = nblk; a.blk_b0 = 0; a.blk_bn = 0;
+    } else if (rq.phase == 1) {
+        a.blk_a0 = 0; a.blk_an = ea; a.blk_b0 = nblk - eb; a.blk_bn = eb;
+    } else {
+        a.blk_a0 = ea; a.blk_an = nblk - ea - eb; a.blk_b0 = 0; a.blk_bn = 0;
+    }
+    a.n_items = (a.blk_an + a.blk_bn) * a.n_strips;
+    if (a.n_items <= 0) return APDE_OK;
     long long grid = (long long)p->sm_count * blocks_per_sm;
     const long long need = (a.n_items + warps_per_block - 1) / warps_per_block;
     if (grid > need) grid = need;
@@ -471,12 +522,12 @@ int launch_pass(apde_plan *p, const StreamArgs &a, cudaStream_t st) {
 }
 
 template <int C, bool NOISE, bool SRC>
-int launch_depth(apde_plan *p, const StreamArgs &a, int td, cudaStream_t st) {
+int launch_depth(apde_plan *p, StreamArgs &a, const BlockReq &rq, int td, cudaStream_t st) {
     switch (td) {
-        case 1: return launch_pass<C, 1, NOISE, SRC>(p, a, st);
-        case 2: return launch_pass<C, 2, NOISE, SRC>(p, a, st);
-        case 3: return launch_pass<C, 3, NOISE, SRC>(p, a, st);
-        case 4: return launch_pass<C, 4, NOISE, SRC>(p, a, st);
+        case 1: return launch_pass<C, 1, NOISE, SRC>(p, a, rq, st);
+        case 2: return launch_pass<C, 2, NOISE, SRC>(p, a, rq, st);
+        case 3: return launch_pass<C, 3, NOISE, SRC>(p, a, rq, st);
+        case 4: return launch_pass<C, 4, NOISE, SRC>(p, a, rq, st);
     }
     set_error("rb_stream: unsupported fused depth %d", td);
     return APDE_EINVAL;
@@ -486,12 +537,12 @@ constexpr int RBS_C1 = 16 / (int)sizeof(T);  // one 16-byte vector per lane
 constexpr int RBS_C2 = 32 / (int)sizeof(T);  // two
 
 template <int C>
-int launch_any(apde_plan *p, const StreamArgs &a, int td, cudaStream_t st) {
+int launch_any(apde_plan *p, StreamArgs &a, const BlockReq &rq, int td, cudaStream_t st) {
     const bool N = p->d.has_noise, S = p->d.has_source;
-    if (N && S) return launch_depth<C, true, true>(p, a, td, st);
-    if (N) return launch_depth<C, true, false>(p, a, td, st);
-    if (S) return launch_depth<C, false, true>(p, a, td, st);
-    return launch_depth<C, false, false>(p, a, td, st);
+    if (N && S) return launch_depth<C, true, true>(p, a, rq, td, st);
+    if (N) return launch_depth<C, true, false>(p, a, rq, td, st);
+    if (S) return launch_depth<C, false, true>(p, a, rq, td, st);
+    return launch_depth<C, false, false>(p, a, rq, td, st);
 }
 
 }  // namespace
@@ -528,31 +579,19 @@ int RBS_FN(apde_plan *p, int64_t n_sweeps, int64_t sweep_base, int phase, cudaSt
         a.row0 = g.row0;
         a.own_lo = g.own_lo;
         a.own_hi = g.own_hi;
-        const long long owned = g.own_hi - g.own_lo;
-        a.rbh = std::max<int64_t>(p->row_block, p->halo);  // an edge block must hold the rows the halo exchange sends
-        const long long nblk = (owned + a.rbh - 1) / a.rbh;
         const int lane_cols = p->lane_vectors == 2 ? RBS_C2 : RBS_C1;
         const int HCA = ((2 * td + lane_cols - 1) / lane_cols) * lane_cols;
         const int VW = 32 * lane_cols - 2 * HCA;
         a.n_strips = (g.cols + VW - 1) / VW;
-        // edge blocks: the leading / trailing row blocks that together hold the `halo` outermost owned
-        // rows on a side with a neighbour strip (those rows are what the halo exchange ships right after
-        // phase 1).  Blocks are rbh >= halo rows, except the last one, which holds the remainder: when
-        // that is shorter than the halo the block before it is an edge block too.
-        const bool top_nb = p->ghost_top > 0, bot_nb = p->ghost_bot > 0;
-        const long long last_rows = owned - (nblk - 1) * a.rbh;
-        long long ea = (top_nb ? 1 : 0), eb = (bot_nb ? (last_rows < p->halo ? 2 : 1) : 0);
-        if (ea + eb > nblk) { ea = std::min<long long>(ea, nblk); eb = nblk - ea; }
-        if (phase == 0) {
-            a.blk_a0 = 0; a.blk_an = nblk; a.blk_b0 = 0; a.blk_bn = 0;
-        } else if (phase == 1) {
-            a.blk_a0 = 0; a.blk_an = ea; a.blk_b0 = nblk - eb; a.blk_bn = eb;
-        } else {
-            a.blk_a0 = ea; a.blk_an = nblk - ea - eb; a.blk_b0 = 0; a.blk_bn = 0;
-        }
-        a.n_items = (a.blk_an + a.blk_bn) * a.n_strips;
-        if (a.n_items > 0) {
-            const int rc = p->lane_vectors == 2 ? launch_any<RBS_C2>(p, a, td, st) : launch_any<RBS_C1>(p, a, td, st);
+        BlockReq rq;
+        rq.owned = g.own_hi - g.own_lo;
+        rq.halo = p->halo;
+        rq.top_nb = p->ghost_top > 0;
+        rq.bot_nb = p->ghost_bot > 0;
+        rq.phase = phase;
+        rq.forced_rbh = p->row_block_forced ? p->row_block : 0;
+        {
+            const int rc = p->lane_vectors == 2 ? launch_any<RBS_C2>(p, a, rq, td, st) : launch_any<RBS_C1>(p, a, rq, td, st);
             if (rc != APDE_OK) return rc;
         }
         if (phase == 1) {

@@ -308,7 +308,7 @@ def roofline_of(ctx, dtype, noise, has_src, depth, rows_per_gpu, cols, glups_per
            "peak_kind": ctx.peak_kind, "kernel": tr.get("kernel", "rb_pipe_kernel / rb_stream_kernel"),
            "algorithmic_bytes_per_lup": bpl,
            "algorithmic_bytes_per_launch": bpl * (rows_per_gpu - 2) * (cols - 2) * depth,
-           "avg_launch_ms": avg_launch_ms,
+           "avg_pass_ms": avg_launch_ms,
            "note": "algorithmic bytes = one read+write of u (+source/links) per sweep; the kernel fuses "
                    f"{depth} sweeps per HBM pass, so frac may exceed 1 while DRAM traffic (ncu, profiles/) stays below peak"}
     if tr.get("dram_bytes_per_launch") and avg_launch_ms:
@@ -364,6 +364,24 @@ def parity_check(ctx):
     return out
 
 
+def passes_per_step(sweeps: int, depth: int) -> int:
+    """Fused passes (= launches of the streaming kernel per strip; two half-launches when a halo exchange is overlapped)."""
+    return -(-sweeps // depth)
+
+
+def bind_to_gpu_numa_node(index: int):
+    """Pin this process to the CPUs next to GPU `index` before it allocates pinned host buffers: with N ranks
+    uploading at once, buffers on the far socket halve the PCIe rate.  Best effort (NVML); returns what it did."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return f"bound to the {len(os.sched_getaffinity(0))} CPUs local to GPU {index}"
+    except Exception as exc:  # no NVML / not permitted: leave the affinity as it is
+        return f"not bound ({type(exc).__name__})"
+
+
 def rb_variant(ctx, name, dtype, grows, cols, noise, has_src, args, scaling):
     """One red-black configuration measured like the headline (device-resident, K timed steps)."""
     depth = default_depth(dtype, noise > 0)
@@ -379,7 +397,7 @@ def rb_variant(ctx, name, dtype, grows, cols, noise, has_src, args, scaling):
                                    f"{args.sweeps} sweeps/step, temporal depth {depth}",
                        "rows_per_gpu": end - begin, "temporal_depth": depth},
             "roofline": roofline_of(ctx, dtype, noise, has_src, depth, end - begin, cols, glups / ctx.world,
-                                    ms / max(launches, 1))}
+                                    ms / (args.variant_steps * passes_per_step(args.sweeps, depth)))}
 
 
 def exact_variant(ctx, k):
@@ -463,6 +481,7 @@ def run_ours(args):
     if not args.no_e2e:
         K = args.e2e_sweeps
         owned = end - begin
+        numa = bind_to_gpu_numa_node(ctx.local) if world > 1 else "single rank: affinity untouched"
         pin = lambda shape: torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy()  # noqa: E731
         lo = max(begin - 2 * args.depth, 0)
         hi = min(end + 2 * args.depth, grows)
@@ -513,7 +532,7 @@ def run_ours(args):
         wall = ctx.max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": (grows - 2) * (args.cols - 2) * K * args.e2e_steps / wall / 1e9, "unit": "GLUP/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "sweeps_per_call": K,
-               "note": api + ", host arrays in pinned memory"}
+               "note": api + ", host arrays in pinned memory", "host_numa": numa}
         del host_u, host_s, host_nh, host_nv
     eng.close()
     _backend.load().apde_release_cache()
@@ -534,9 +553,8 @@ def run_ours(args):
                 variants.append(rb_variant(ctx, name, dtype, 65536, 65536, 0.01, True, args, "strong"))
 
     if rank == 0:
-        n_sweep_launches = max(launches, 1)
         roofline = roofline_of(ctx, args.dtype, args.noise, has_src, args.depth, args.rows, args.cols, glups / world,
-                               ms / n_sweep_launches, single)
+                               ms / (args.steps * passes_per_step(args.sweeps, args.depth)), single)
         out = {"metric": "GLUP/s", "value": glups, "unit": "GLUP/s", "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": args.dtype, "data": "synthetic (device-generated sin source, zero ring)",
