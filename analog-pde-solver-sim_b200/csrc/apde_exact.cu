@@ -341,19 +341,15 @@ struct K2Params {
     long long n_sweeps;             // sweeps in this launch
 };
 
-#ifndef K2_SMALL_THREADS
-#define K2_SMALL_THREADS 512  // CTA size of the two-CTAs-per-SM configuration
-#endif
-#ifndef K2_SMALL_MINBLOCKS
-#define K2_SMALL_MINBLOCKS 2
-#endif
-// MAXT / MINB only shape the register budget (__launch_bounds__): <1024,1> and <512,2> get 64 registers,
-// <384,2> 85, <256,2> 128.
+// MAXT is THE block size (the launch must use exactly MAXT threads: the node stride of a thread is a compile-time
+// constant so that a thread's further nodes are reached with immediate offsets); MINB shapes the register budget:
+// <1024,1> and <512,2> get 64 registers, <256,2> 128.
 template <bool HAS_NOISE, bool HAS_SRC, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) exact_ring_kernel(K2Params p) {
     const int rows = p.rows, cols = p.cols;
     const long long P = p.P;
-    const int G = gridDim.x, c = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+    constexpr int nthr = MAXT;
+    const int G = gridDim.x, c = blockIdx.x, tid = threadIdx.x;
     const int dmax = rows + cols - 4;
     const long long ND = dmax - 1;  // diagonals 2..dmax
     const int pred = (c + G - 1) % G;
@@ -375,28 +371,48 @@ __global__ void __launch_bounds__(MAXT, MINB) exact_ring_kernel(K2Params p) {
         };
         if (t > 0 && tid == 0) wait_pred(2);
         __syncthreads();
+        // Element offset of this thread's first node of diagonal d, (d*P + ilo + tid), advanced incrementally: the
+        // seven operand rows of a node (u on diagonals d-1, d, d+1; links and source on d-1 and d) then sit at fixed
+        // offsets from it and the thread's further nodes nthr elements on -- no per-node 64-bit address arithmetic
+        // (which, at 64 registers, used to be recomputed and spilled for every node).
+        long long off = 2 * P + max(1, 2 - (cols - 2)) + tid;
         for (int d = 2; d <= dmax; ++d) {
             const int ilo = max(1, d - (cols - 2)), ihi = min(rows - 2, d - 1);
-            const double *up = U + (long long)(d - 1) * P;  // diagonal d-1: north/west, this sweep
-            const double *dn = U + (long long)(d + 1) * P;  // diagonal d+1: south/east, previous sweep
-            double *me = U + (long long)d * P;
-            for (int i = ilo + tid; i <= ihi; i += nthr) {
-                const double un = __ldcg(up + i - 1), uw = __ldcg(up + i);
-                const double us = __ldcg(dn + i + 1), ue = __ldcg(dn + i);
-                const double old = __ldcg(me + i);
-                double2 ln = {1.0, 1.0}, ls = ln, lw = ln, le = ln;
-                double sv = 0.0;
-                if (HAS_NOISE) {
-                    ln = __ldg(p.LV + (long long)(d - 1) * P + i - 1);
-                    lw = __ldg(p.LH + (long long)(d - 1) * P + i);
-                    ls = __ldg(p.LV + (long long)d * P + i);
-                    le = __ldg(p.LH + (long long)d * P + i);
+            const double *me0 = U + off;            // (d, i)
+            const double *up0 = me0 - P;            // (d-1, i): west; [-1]: north
+            const double *dn0 = me0 + P;            // (d+1, i): east; [+1]: south
+            const double2 *lvd0 = p.LV + off, *lhd0 = p.LH + off;          // links of diagonal d   : south, east
+            const double2 *lvu0 = lvd0 - P, *lhu0 = lhd0 - P;              // links of diagonal d-1 : [-1] north, west
+            const double *s0 = p.S + off;
+            constexpr int NPT = 4;  // nodes per thread per unrolled chunk
+            for (int ib = ilo + tid; ib <= ihi; ib += NPT * nthr) {
+                const long long cb = ib - (ilo + tid);  // element distance of this chunk from the thread's first node
+                const double *up = up0 + cb, *dn = dn0 + cb, *sp = s0 + cb;
+                double *me = const_cast<double *>(me0) + cb;
+                const double2 *lvu = lvu0 + cb, *lhu = lhu0 + cb, *lvd = lvd0 + cb, *lhd = lhd0 + cb;
+#pragma unroll
+                for (int e = 0; e < NPT; ++e) {
+                    if (ib + e * nthr > ihi) break;
+                    const int k = e * nthr;  // compile-time: immediate address offsets
+                    const double un = __ldcg(up + k - 1), uw = __ldcg(up + k);
+                    const double us = __ldcg(dn + k + 1), ue = __ldcg(dn + k);
+                    const double old = __ldcg(me + k);
+                    double2 ln = {1.0, 1.0}, ls = ln, lw = ln, le = ln;
+                    double sv = 0.0;
+                    if (HAS_NOISE) {
+                        ln = __ldg(lvu + k - 1);
+                        lw = __ldg(lhu + k);
+                        ls = __ldg(lvd + k);
+                        le = __ldg(lhd + k);
+                    }
+                    if (HAS_SRC) sv = __ldg(sp + k);
+                    const double nw = relax_node<HAS_NOISE, HAS_SRC>(un, us, uw, ue, ln, ls, lw, le, sv);
+                    mx = max_ignore_nan(mx, fabs(__dsub_rn(nw, old)));
+                    __stcg(me + k, nw);
                 }
-                if (HAS_SRC) sv = __ldg(p.S + (long long)d * P + i);
-                const double nw = relax_node<HAS_NOISE, HAS_SRC>(un, us, uw, ue, ln, ls, lw, le, sv);
-                mx = max_ignore_nan(mx, fabs(__dsub_rn(nw, old)));
-                __stcg(me + i, nw);
             }
+            // next diagonal: one pitch further, and one node further once the diagonal starts at the east column
+            off += P + (max(1, d + 1 - (cols - 2)) - ilo);
             if (t > 0 && tid == 0 && d < dmax) wait_pred(d + 1);
             __syncthreads();
             if (tid == 0)
@@ -644,9 +660,10 @@ struct RingCfg {
 
 template <bool N, bool S>
 static const void *ring_fn(int npt) {
-    switch (npt) {
-        case 0: return (const void *)exact_ring_kernel<N, S, 1024, 1>;
-        case -1: return (const void *)exact_ring_kernel<N, S, K2_SMALL_THREADS, K2_SMALL_MINBLOCKS>;
+    switch (npt) {  // <= 0: generic kernel K2, the code is minus the block size
+        case -1024: return (const void *)exact_ring_kernel<N, S, 1024, 1>;
+        case -512: return (const void *)exact_ring_kernel<N, S, 512, 2>;
+        case -256: return (const void *)exact_ring_kernel<N, S, 256, 2>;
         case 1: return (const void *)exact_ring2_kernel<N, S, 1>;
         case 2: return (const void *)exact_ring2_kernel<N, S, 2>;
         case 4: return (const void *)exact_ring2_kernel<N, S, 4>;
@@ -696,10 +713,12 @@ static int ring_configure(bool noise, bool src, int64_t rows, int64_t cols, int6
         cfg->smem = smem2;
         if (const char *v = getenv("APDE_RING_BATCH")) cfg->kb = std::max(1, atoi(v));
     } else {
-        cfg->block = maxdiag > 2048 ? (many ? K2_SMALL_THREADS : 1024) : (maxdiag > 512 ? 512 : 256);
-        if (const char *v = getenv("APDE_RING_BLOCK")) cfg->block = std::min(1024, std::max(64, atoi(v) / 32 * 32));
-        // npt 0: kernel compiled for 1024-thread CTAs; -1: for K2_SMALL_THREADS-thread CTAs (more registers)
-        cfg->npt = cfg->block <= K2_SMALL_THREADS ? -1 : 0;
+        cfg->block = maxdiag > 2048 ? (many ? 512 : 1024) : (maxdiag > 512 ? 512 : 256);
+        if (const char *v = getenv("APDE_RING_BLOCK")) {
+            const int b = atoi(v);
+            cfg->block = b >= 1024 ? 1024 : (b >= 512 ? 512 : 256);  // the block sizes the kernel is instantiated for
+        }
+        cfg->npt = -cfg->block;
         cfg->smem = 0;
     }
     const void *fn = ring_fn(noise, src, cfg->npt);
