@@ -141,7 +141,7 @@ def default_temporal_depth(dtype: str, has_noise: bool) -> int:
 
 
 def multigrid_levels(rows: int, cols: int) -> int:
-    """Number of grid levels a V-cycle gets on a rows x cols grid (1 = the shape does not coarsen)."""
+    """Number of grid levels a V-cycle gets on a rows x cols grid (1 = too small to coarsen)."""
     return int(load().apde_multigrid_levels(int(rows), int(cols)))
 
 

@@ -7,10 +7,10 @@
 //     smooth nu1 sweeps (red-black, fused kernel)  ->  residual r = -src - 4u + sum(neighbours)
 //     -> restrict to the next coarser grid (full weighting transposed, src_c = -P^T r; rediscretised 5-point operator)
 //     -> recurse with a zero initial error -> prolong the coarse error bilinearly and add it -> smooth nu2 sweeps.
-// Vertex-centred coarsening: a level of (r, c) nodes coarsens to ((r-1)/2+1, (c-1)/2+1) while both r-1 and c-1 are
-// even and the coarse grid keeps at least 3 nodes per direction; the coarsest level is relaxed by a fixed number of
-// sweeps.  Grids of 2^k+1 nodes per side coarsen all the way down; a side like 4096 (r-1 odd) does not coarsen at
-// all, and the solve is refused (use redblack_sor there).
+// Coarsening: a level of (r, c) nodes coarsens to ((r+1)/2, (c+1)/2) uniform nodes over the same rectangle while both
+// stay >= 3: every second node when the side has 2^k+1-like sizes (nested, spacing ratio exactly 2), otherwise a
+// non-nested grid with ratio slightly above 2 (4096 -> 2048 -> 1024 ...); the transfers are hat-function weights
+// computed from the node positions, so every size works.  The coarsest level is relaxed by a fixed number of sweeps.
 //
 // Every level is an ordinary apde_plan (padded strip layout, plan dtype), so the smoother is literally
 // plan_run(); the two transfer kernels below work between plans.  All arithmetic is explicit round-to-nearest with a
@@ -36,56 +36,69 @@ __device__ __forceinline__ T mg_residual(const T *__restrict__ u, const T *__res
     return t;
 }
 
-// coarse source: src_c(I,J) = -( 0.5*rowsum(2I-1) + rowsum(2I) + 0.5*rowsum(2I+1) ),
-// rowsum(i) = (0.5*r(i,2J-1) + r(i,2J)) + 0.5*r(i,2J+1); coarse u = 0 everywhere (zero initial error, zero ring)
+// ---- grid transfer with hat-function weights ---------------------------------------------------------------
+// Fine node f and coarse node I of one direction sit at f*h and I*H over the same length, H/h = r =
+// (n_fine-1)/(n_coarse-1) (exactly 2 for nested grids, 2.0005 for 4096 -> 2048).  P[f][I] = max(0, 1 - |f/r - I|)
+// is linear interpolation; restriction is its transpose.  With the rediscretised 5-point operator the coarse
+// equation [4,-1] e = (H^2/h^2) * (P^T r / (r_x r_y)) reduces to [4,-1] e = P^T r, i.e. src_c = -P^T r (for r = 2
+// the weights are 1, 1/2, 1/4: full weighting times 4).  Weights are computed in fp64 from integer positions by the
+// same expression on the device and in the CPU statement; sums run over ascending fine indices, rows outer.
+__device__ __forceinline__ double mg_hat(int f, int I, double inv_r) {
+    return fmax(0.0, __dsub_rn(1.0, fabs(__dsub_rn(__dmul_rn((double)f, inv_r), (double)I))));
+}
+
+// coarse source src_c(I,J) = -sum_f sum_g P[f][I] P[g][J] r(f,g); coarse u = 0 everywhere (zero initial error, zero ring)
 template <typename T>
 __global__ void mg_restrict_kernel(const T *__restrict__ uf, const T *__restrict__ sf, long long pitch_f, long long padl_f,
                                    int rows_f, int cols_f, T *__restrict__ uc0, T *__restrict__ uc1, T *__restrict__ sc,
-                                   long long pitch_c, long long padl_c, int rows_c, int cols_c) {
+                                   long long pitch_c, long long padl_c, int rows_c, int cols_c, double inv_rx, double inv_ry,
+                                   double rx, double ry) {
     const long long n = (long long)rows_c * cols_c;
     for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
         const int I = (int)(k / cols_c), J = (int)(k - (long long)I * cols_c);
         const long long cc = (long long)I * pitch_c + padl_c + J;
         uc0[cc] = (T)0;
         uc1[cc] = (T)0;
-        T out = (T)0;
+        double acc = 0.0;
         if (I > 0 && I < rows_c - 1 && J > 0 && J < cols_c - 1) {
-            T rs[3];
-#pragma unroll
-            for (int d = -1; d <= 1; ++d) {
-                const int i = 2 * I + d;
-                T r3[3];
-#pragma unroll
-                for (int e = -1; e <= 1; ++e) {
-                    const int j = 2 * J + e;
-                    const bool interior = i > 0 && i < rows_f - 1 && j > 0 && j < cols_f - 1;
-                    r3[e + 1] = interior ? mg_residual<T>(uf, sf, (long long)i * pitch_f + padl_f + j, pitch_f) : (T)0;
+            // fine nodes with a non-zero weight lie strictly inside (r*(I-1), r*(I+1))
+            const int f0 = max(1, (int)floor(rx * (I - 1))), f1 = min(rows_f - 2, (int)ceil(rx * (I + 1)));
+            const int g0 = max(1, (int)floor(ry * (J - 1))), g1 = min(cols_f - 2, (int)ceil(ry * (J + 1)));
+            for (int f = f0; f <= f1; ++f) {
+                const double wf = mg_hat(f, I, inv_rx);
+                if (wf == 0.0) continue;
+                double row = 0.0;
+                for (int g = g0; g <= g1; ++g) {
+                    const double wg = mg_hat(g, J, inv_ry);
+                    if (wg == 0.0) continue;
+                    const double r = (double)mg_residual<T>(uf, sf, (long long)f * pitch_f + padl_f + g, pitch_f);
+                    row = __dadd_rn(row, __dmul_rn(wg, r));
                 }
-                rs[d + 1] = Ar<T>::add(Ar<T>::add(Ar<T>::mul((T)0.5, r3[0]), r3[1]), Ar<T>::mul((T)0.5, r3[2]));
+                acc = __dadd_rn(acc, __dmul_rn(wf, row));
             }
-            const T b = Ar<T>::add(Ar<T>::add(Ar<T>::mul((T)0.5, rs[0]), rs[1]), Ar<T>::mul((T)0.5, rs[2]));
-            out = -b;
         }
-        sc[cc] = out;
+        sc[cc] = (T)(-acc);
     }
 }
 
-// fine u += P e  (bilinear): even/even copy, one odd index the mean of two, both odd 0.25*(((e00+e01)+e10)+e11)
+// fine u += P e: bilinear between the coarse nodes I0 = floor(f/r), I0+1 (rows first, then columns)
 // corr_max (optional): max |P e| over the interior, max-accumulated on the bit pattern (for the stop criterion)
 template <typename T>
 __global__ void mg_prolong_kernel(T *__restrict__ uf, long long pitch_f, long long padl_f, int rows_f, int cols_f,
-                                  const T *__restrict__ ec, long long pitch_c, long long padl_c, T *corr_max) {
+                                  const T *__restrict__ ec, long long pitch_c, long long padl_c, int rows_c, int cols_c,
+                                  double inv_rx, double inv_ry, T *corr_max) {
     const long long n = (long long)(rows_f - 2) * (cols_f - 2);
     T mx = (T)0;
     for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
         const int i = 1 + (int)(k / (cols_f - 2)), j = 1 + (int)(k - (long long)(i - 1) * (cols_f - 2));
-        const int I = i >> 1, J = j >> 1;
+        const double xi = __dmul_rn((double)i, inv_rx), xj = __dmul_rn((double)j, inv_ry);
+        const int I = min((int)floor(xi), rows_c - 2), J = min((int)floor(xj), cols_c - 2);
+        const double ti = __dsub_rn(xi, (double)I), tj = __dsub_rn(xj, (double)J);
         const T *e = ec + (long long)I * pitch_c + padl_c + J;
-        T corr;
-        if (!(i & 1) && !(j & 1)) corr = e[0];
-        else if (!(i & 1)) corr = Ar<T>::mul((T)0.5, Ar<T>::add(e[0], e[1]));
-        else if (!(j & 1)) corr = Ar<T>::mul((T)0.5, Ar<T>::add(e[0], e[pitch_c]));
-        else corr = Ar<T>::mul((T)0.25, Ar<T>::add(Ar<T>::add(Ar<T>::add(e[0], e[1]), e[pitch_c]), e[pitch_c + 1]));
+        // top = (1-tj)*e00 + tj*e01 ; bot likewise on the next coarse row ; corr = (1-ti)*top + ti*bot
+        const double top = __dadd_rn(__dmul_rn(__dsub_rn(1.0, tj), (double)e[0]), __dmul_rn(tj, (double)e[1]));
+        const double bot = __dadd_rn(__dmul_rn(__dsub_rn(1.0, tj), (double)e[pitch_c]), __dmul_rn(tj, (double)e[pitch_c + 1]));
+        const T corr = (T)__dadd_rn(__dmul_rn(__dsub_rn(1.0, ti), top), __dmul_rn(ti, bot));
         const long long c = (long long)i * pitch_f + padl_f + j;
         uf[c] = Ar<T>::add(uf[c], corr);
         mx = max_ignore_nan(mx, Ar<T>::abs(corr));
@@ -107,8 +120,10 @@ struct Level {
 template <typename T>
 int restrict_to(apde_plan *f, apde_plan *c) {
     const int tg = f->sm_count * 8;
+    const double rx = (double)(f->d.grows - 1) / (double)(c->d.grows - 1), ry = (double)(f->d.cols - 1) / (double)(c->d.cols - 1);
     mg_restrict_kernel<T><<<tg, 256>>>(f->U<T>(f->cur), f->S<T>(), f->pitch, f->padl, (int)f->d.grows, (int)f->d.cols,
-                                       c->U<T>(0), c->U<T>(1), c->S<T>(), c->pitch, c->padl, (int)c->d.grows, (int)c->d.cols);
+                                       c->U<T>(0), c->U<T>(1), c->S<T>(), c->pitch, c->padl, (int)c->d.grows, (int)c->d.cols,
+                                       1.0 / rx, 1.0 / ry, rx, ry);
     APDE_CUDA(cudaGetLastError());
     c->cur = 0;
     c->pass_open = false;
@@ -124,8 +139,10 @@ int prolong_from(apde_plan *f, apde_plan *c, bool want_max) {
         corr_max = reinterpret_cast<T *>(static_cast<char *>(f->scratch.p) + 40);
         APDE_CUDA(cudaMemsetAsync(corr_max, 0, sizeof(T), 0));
     }
+    const double rx = (double)(f->d.grows - 1) / (double)(c->d.grows - 1), ry = (double)(f->d.cols - 1) / (double)(c->d.cols - 1);
     mg_prolong_kernel<T><<<tg, 256>>>(f->U<T>(f->cur), f->pitch, f->padl, (int)f->d.grows, (int)f->d.cols,
-                                      c->U<T>(c->cur), c->pitch, c->padl, corr_max);
+                                      c->U<T>(c->cur), c->pitch, c->padl, (int)c->d.grows, (int)c->d.cols, 1.0 / rx, 1.0 / ry,
+                                      corr_max);
     APDE_CUDA(cudaGetLastError());
     f->launches++;
     return APDE_OK;
@@ -133,11 +150,14 @@ int prolong_from(apde_plan *f, apde_plan *c, bool want_max) {
 
 }  // namespace
 
+// A level of n nodes per side coarsens to (n + 1) / 2: nested (every second node) when n - 1 is even, otherwise a
+// uniform grid over the same length with a spacing ratio slightly above 2 (4096 -> 2048: 4095/2047).
+int64_t mg_coarse_size(int64_t n) { return (n + 1) / 2; }
 int mg_level_count(int64_t rows, int64_t cols) {
     int n = 1;
-    while ((rows - 1) % 2 == 0 && (cols - 1) % 2 == 0 && (rows - 1) / 2 + 1 >= 3 && (cols - 1) / 2 + 1 >= 3) {
-        rows = (rows - 1) / 2 + 1;
-        cols = (cols - 1) / 2 + 1;
+    while (rows > 3 && cols > 3 && mg_coarse_size(rows) >= 3 && mg_coarse_size(cols) >= 3) {
+        rows = mg_coarse_size(rows);
+        cols = mg_coarse_size(cols);
         ++n;
     }
     return n;
@@ -165,12 +185,6 @@ int solve_multigrid(int elem, double *grid, const double *src, int64_t rows, int
     if (nu2 <= 0) nu2 = 2;
     if (coarse_sweeps <= 0) coarse_sweeps = 32;
     const int n_levels = mg_level_count(rows, cols);
-    if (n_levels < 2 && std::max(rows, cols) > 9) {
-        set_error("multigrid: a %lld x %lld grid does not coarsen (rows-1 and cols-1 must be even; 2^k+1 nodes per side "
-                  "coarsen fully) -- use the redblack_sor mode for this size",
-                  (long long)rows, (long long)cols);
-        return APDE_EINVAL;
-    }
     release_cached_plan();
     std::vector<std::unique_ptr<Level>> lv;
     int64_t r = rows, c = cols;
@@ -189,8 +203,8 @@ int solve_multigrid(int elem, double *grid, const double *src, int64_t rows, int
         L->rows = (int)r;
         L->cols = (int)c;
         lv.push_back(std::move(L));
-        r = (r - 1) / 2 + 1;
-        c = (c - 1) / 2 + 1;
+        r = mg_coarse_size(r);
+        c = mg_coarse_size(c);
     }
     apde_plan *fine = lv[0]->plan;
     APDE_TRY(plan_upload(fine, grid, nullptr, nullptr, src));

@@ -113,10 +113,11 @@ int apde_solve_redblack_ex(int dtype_bytes, double *grid, const double *noise_h,
 /* ------------------------------------------------------------------------------------------
  * MULTIGRID (not in the reference) -- geometric V(nu1, nu2) cycles for the ideal mesh
  * (no link mismatch: DigitalSolver, or AnalogPDESolver with noise_level 0), the fused red-black kernels as smoother,
- * full-weighting restriction, bilinear prolongation, rediscretised 5-point operator on every level.  Vertex-centred
- * coarsening: a level coarsens while rows-1 and cols-1 are even (2^k+1 nodes per side coarsen fully);
- * apde_multigrid_levels() says how many levels a shape gets, and a shape that does not coarsen at all is refused with
- * APDE_EINVAL (use apde_solve_redblack_ex with omega there).
+ * restriction = transpose of the (bi)linear prolongation, rediscretised 5-point operator on every level.  A level of n
+ * nodes per side coarsens to (n+1)/2 uniform nodes over the same length while both sides keep >= 3 nodes: nested
+ * (every second node) for 2^k+1-like sides, otherwise non-nested with a spacing ratio slightly above 2 (4096 -> 2048),
+ * the transfer weights being hat functions of the node positions -- every grid size works;
+ * apde_multigrid_levels() says how many levels a shape gets.
  * A cycle costs about (nu1 + nu2) * 4/3 fine-grid sweeps and reduces the error by a factor independent of the grid
  * size.  residual_history[c] bounds how far cycle c moved any node: the sum of its fine-grid smoothing sweeps' max_change
  * and of max |coarse-grid correction|; the solve stops after the first cycle where that is < tol (the reference's

@@ -175,18 +175,27 @@ def red_black(grid, noise_h=None, noise_v=None, source=None, n_sweeps: int = 1,
 
 def _mg_levels(rows, cols):
     n = 1
-    while (rows - 1) % 2 == 0 and (cols - 1) % 2 == 0 and (rows - 1) // 2 + 1 >= 3 and (cols - 1) // 2 + 1 >= 3:
-        rows, cols = (rows - 1) // 2 + 1, (cols - 1) // 2 + 1
+    while rows > 3 and cols > 3 and (rows + 1) // 2 >= 3 and (cols + 1) // 2 >= 3:
+        rows, cols = (rows + 1) // 2, (cols + 1) // 2
         n += 1
     return n
+
+
+def _mg_hat_matrix(n_fine, n_coarse):
+    """P[f, I] = max(0, 1 - |f * (1/r) - I|), r = (n_fine-1)/(n_coarse-1): the device's mg_hat, in fp64."""
+    inv_r = 1.0 / ((n_fine - 1) / (n_coarse - 1))
+    f = np.arange(n_fine, dtype=np.float64)[:, None]
+    big_i = np.arange(n_coarse, dtype=np.float64)[None, :]
+    return np.maximum(0.0, 1.0 - np.abs(f * inv_r - big_i))
 
 
 def multigrid(grid, source=None, tol: float = 1e-8, max_cycles: int = 50, nu1: int = 2, nu2: int = 2,
               coarse_sweeps: int = 32, dtype=np.float64):
     """CPU statement of csrc/apde_multigrid.cu (NOT in the reference): V(nu1, nu2) cycles on the ideal mesh,
-    red-black smoothing (red_black above), r = ((((uN+uS)+uW)+uE) - 4u) - src, coarse source
-    -((0.5*rs(2I-1) + rs(2I)) + 0.5*rs(2I+1)) with rs(i) = (0.5*r(i,2J-1) + r(i,2J)) + 0.5*r(i,2J+1), bilinear
-    prolongation 0.5*(a+b) / 0.25*(((a+b)+c)+d); same association everywhere, so results match the GPU bit for bit.
+    red-black smoothing (red_black above), r = ((((uN+uS)+uW)+uE) - 4u) - src, levels of ((n+1)//2) nodes per side,
+    hat-function transfer weights from the node positions (restriction = transpose of linear interpolation, sums over
+    ascending fine indices, rows outer; prolongation rows of the coarse cell first) -- the same association as the
+    device code, all transfer arithmetic in fp64, so results match the GPU bit for bit.
     Per cycle the history holds an upper bound of how far the cycle moved any fine node: the fp64 sum, in order, of the
     pre-smoothing sweeps' max_change, max |coarse-grid correction| and the post-smoothing sweeps' max_change.
     Returns (grid in dtype, that history, cycles)."""
@@ -195,34 +204,51 @@ def multigrid(grid, source=None, tol: float = 1e-8, max_cycles: int = 50, nu1: i
     rows, cols = u.shape
     src = None if source is None else np.asarray(source, dtype=np.float64).astype(dtype)
     L = _mg_levels(rows, cols)
-    half, quarter, four = dt(0.5), dt(0.25), dt(4)
+    four = dt(4)
 
     def smooth(uu, ss, n):
         out, h, _ = red_black(uu.astype(np.float64), None, None, None if ss is None else ss.astype(np.float64), n, dtype=dtype)
         return out, h
 
     def restrict(uu, ss):
-        r = np.zeros_like(uu)
+        r = np.zeros(uu.shape, dtype=np.float64)
         t = (uu[:-2, 1:-1] + uu[2:, 1:-1])
         t = t + uu[1:-1, :-2]
         t = t + uu[1:-1, 2:]
         t = t - four * uu[1:-1, 1:-1]
         if ss is not None:
             t = t - ss[1:-1, 1:-1]
-        r[1:-1, 1:-1] = t
-        rc, cc = (uu.shape[0] - 1) // 2 + 1, (uu.shape[1] - 1) // 2 + 1
-        rs = (half * r[:, 1:-2:2] + r[:, 2:-1:2]) + half * r[:, 3::2]          # columns J = 1 .. cc-2
-        b = (half * rs[1:-2:2] + rs[2:-1:2]) + half * rs[3::2]                  # rows    I = 1 .. rc-2
+        r[1:-1, 1:-1] = t.astype(np.float64)
+        nf_r, nf_c = uu.shape
+        rc, cc = (nf_r + 1) // 2, (nf_c + 1) // 2
+        pr, pc = _mg_hat_matrix(nf_r, rc), _mg_hat_matrix(nf_c, cc)
+        # row[f, J] = sum_g (ascending, zero weights skipped) P[g, J] * r[f, g]; acc[I, J] = sum_f P[f, I] * row[f, J]
+        row = np.zeros((nf_r, cc))
+        for g in range(1, nf_c - 1):
+            js = np.nonzero(pc[g])[0]
+            for j in js:
+                row[:, j] = row[:, j] + pc[g, j] * r[:, g]
+        acc = np.zeros((rc, cc))
+        for f in range(1, nf_r - 1):
+            for i in np.nonzero(pr[f])[0]:
+                acc[i, :] = acc[i, :] + pr[f, i] * row[f, :]
         sc = np.zeros((rc, cc), dtype=dtype)
-        sc[1:-1, 1:-1] = -b
+        sc[1:-1, 1:-1] = (-acc[1:-1, 1:-1]).astype(dtype)
         return sc
 
     def prolong(uu, e, stats=None):
-        corr = np.zeros_like(uu)
-        corr[::2, ::2] = e
-        corr[::2, 1::2] = half * (e[:, :-1] + e[:, 1:])
-        corr[1::2, ::2] = half * (e[:-1, :] + e[1:, :])
-        corr[1::2, 1::2] = quarter * (((e[:-1, :-1] + e[:-1, 1:]) + e[1:, :-1]) + e[1:, 1:])
+        nf_r, nf_c = uu.shape
+        rc, cc = e.shape
+        inv_rx, inv_ry = 1.0 / ((nf_r - 1) / (rc - 1)), 1.0 / ((nf_c - 1) / (cc - 1))
+        xi, xj = np.arange(nf_r, dtype=np.float64) * inv_rx, np.arange(nf_c, dtype=np.float64) * inv_ry
+        bi, bj = np.minimum(np.floor(xi).astype(int), rc - 2), np.minimum(np.floor(xj).astype(int), cc - 2)
+        ti, tj = (xi - bi)[:, None], (xj - bj)[None, :]
+        ed = e.astype(np.float64)
+        e00, e01 = ed[bi][:, bj], ed[bi][:, bj + 1]
+        e10, e11 = ed[bi + 1][:, bj], ed[bi + 1][:, bj + 1]
+        top = (1.0 - tj) * e00 + tj * e01
+        bot = (1.0 - tj) * e10 + tj * e11
+        corr = ((1.0 - ti) * top + ti * bot).astype(dtype)
         out = uu.copy()
         out[1:-1, 1:-1] = uu[1:-1, 1:-1] + corr[1:-1, 1:-1]
         if stats is not None:

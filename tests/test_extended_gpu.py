@@ -137,19 +137,16 @@ def test_extended_update_on_two_strips_equals_one_strip(dt):
 
 
 # ---- multigrid V-cycle (csrc/apde_multigrid.cu) ---------------------------------------------------------------
-@pytest.mark.parametrize("rows,cols", [(5, 5), (9, 17), (17, 17), (33, 65), (129, 129), (97, 49), (20, 20)])
+@pytest.mark.parametrize("rows,cols", [(5, 5), (9, 17), (17, 17), (33, 65), (129, 129), (97, 49), (20, 20), (64, 50), (100, 37), (4, 7)])
 @pytest.mark.parametrize("with_src", [True, False])
 @pytest.mark.parametrize("mode,dt", [("multigrid", np.float64), ("multigrid32", np.float32)])
 def test_vcycle_bit_exact_vs_its_cpu_statement(rows, cols, with_src, mode, dt):
     """Fixed number of V(2,2) cycles: grid and per-cycle residuals equal oracle.multigrid (numpy + the red-black
     checker) bit for bit -- smoothing, residual, restriction and prolongation all use one fixed association.
-    97 x 49 coarsens 4 times, 20 x 20 not at all (then a 'cycle' is nu1+nu2 sweeps) -- only allowed because it is tiny."""
+    Nested sizes (2^k+1: spacing ratio exactly 2) and non-nested ones (20 -> 10 -> 5 -> 3, 64 x 50, 100 x 37: ratios
+    19/9, 63/31, ...; different in the two directions) go through the same hat-weight transfers; 4 x 7 has one level."""
     g0, _, _, s = random_problem(rows, cols, 0.0, seed=rows + 7 * cols, with_source=with_src)
     want, wh, wc = oracle.multigrid(g0, s, 0.0, 3, dtype=dt)
-    if rows == 20:
-        with pytest.raises(_backend.ApdeError):
-            _backend.solve(mode, g0.copy(), None, None, s, 0.0, 3)
-        return
     g = g0.copy()
     hist, n, _ = _backend.solve(mode, g, None, None, s, 0.0, 3)
     assert n == wc == 3
@@ -161,7 +158,7 @@ def test_vcycle_converges_in_a_handful_of_cycles_at_any_size():
     """Poisson with the known solution sin(pi x) sin(pi y) (examples/poisson_demo.py upstream), N = 65 ... 2049: the
     cycle count to tol 1e-10 (per-cycle movement) does not grow with N (Gauss-Seidel needs ~N^2 sweeps), and the answer is the discrete
     solution: the error vs the exact PDE solution shrinks like h^2 (second-order discretisation)."""
-    errs, cycles, sizes = [], [], (65, 257, 1025, 2049)
+    errs, cycles, sizes = [], [], (65, 256, 1025, 2048)
     for n in sizes:
         x = np.arange(n) / (n - 1)
         exact = np.outer(np.sin(np.pi * x), np.sin(np.pi * x))
@@ -171,11 +168,12 @@ def test_vcycle_converges_in_a_handful_of_cycles_at_any_size():
         assert len(d.residual_history) == d.iterations_run
         cycles.append(d.iterations_run)
         errs.append(np.max(np.abs(u - exact)))
-    assert max(cycles) <= 12 and max(cycles) - min(cycles) <= 2
+    assert max(cycles) <= 16 and max(cycles) - min(cycles) <= 6     # non-nested levels (256, 2048) contract a little slower
     for (n1, a), (n2, b) in zip(zip(sizes, errs), zip(sizes[1:], errs[1:])):
         want = ((n2 - 1) / (n1 - 1)) ** 2        # second order: error ~ h^2
         assert 0.85 * want < a / b < 1.15 * want
-    assert _backend.multigrid_levels(2049, 2049) == 11 and _backend.multigrid_levels(4096, 4096) == 1
+    assert _backend.multigrid_levels(2049, 2049) == 11 and _backend.multigrid_levels(4096, 4096) == 11
+    assert _backend.multigrid_levels(4, 7) == 1 and _backend.multigrid_levels(20, 20) == 4
 
 
 def test_vcycle_matches_the_reference_answer_and_rejects_what_it_cannot_do():
@@ -186,8 +184,13 @@ def test_vcycle_matches_the_reference_answer_and_rejects_what_it_cannot_do():
     g0[0, :] = 1.0
     ref, _, it = oracle.gauss_seidel(g0, None, None, None, 1e-14, 400_000)
     assert d.iterations_run < 20 < it and np.max(np.abs(u - ref)) <= 1e-10
-    with pytest.raises(_backend.ApdeError, match="does not coarsen"):
-        DigitalSolver(rows=4096, cols=64).solve(top_hot, mode="multigrid")
+    # a long thin grid: the short side stops coarsening early, the V-cycle still converges
+    thin = DigitalSolver(rows=1024, cols=40)
+    ut = thin.solve(top_hot, tol=1e-12, max_iter=200, mode="multigrid")
+    g1 = np.zeros((1024, 40))
+    g1[0, :] = 1.0
+    rt, _, _ = oracle.gauss_seidel(g1, None, None, None, 1e-14, 400_000)
+    assert thin.iterations_run < 200 and np.max(np.abs(ut - rt)) <= 1e-9
     with pytest.raises(ValueError, match="ideal mesh"):
         AnalogPDESolver(rows=33, cols=33, noise_level=0.01, rng_seed=1).solve(top_hot, mode="multigrid")
     a = AnalogPDESolver(rows=33, cols=33)       # noise_level 0: the ideal mesh, allowed
