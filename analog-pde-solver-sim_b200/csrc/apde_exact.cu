@@ -344,7 +344,10 @@ struct K2Params {
 // MAXT is THE block size (the launch must use exactly MAXT threads: the node stride of a thread is a compile-time
 // constant so that a thread's further nodes are reached with immediate offsets); MINB shapes the register budget:
 // <1024,1> and <512,2> get 64 registers, <256,2> 128.
-template <bool HAS_NOISE, bool HAS_SRC, int MAXT, int MINB>
+// NB = nodes whose operands a thread requests before it relaxes any of them (nodes of one diagonal are independent):
+// their L2 round trips overlap.  A node has 5 (+1 source, +8 for the four {b, 1/b} links) operand doubles, so NB is
+// what the register budget of the launch shape allows: 4 without links, 1 with links at 64 registers, 4 at 128.
+template <bool HAS_NOISE, bool HAS_SRC, int MAXT, int MINB, int NB>
 __global__ void __launch_bounds__(MAXT, MINB) exact_ring_kernel(K2Params p) {
     const int rows = p.rows, cols = p.cols;
     const long long P = p.P;
@@ -384,31 +387,42 @@ __global__ void __launch_bounds__(MAXT, MINB) exact_ring_kernel(K2Params p) {
             const double2 *lvd0 = p.LV + off, *lhd0 = p.LH + off;          // links of diagonal d   : south, east
             const double2 *lvu0 = lvd0 - P, *lhu0 = lhd0 - P;              // links of diagonal d-1 : [-1] north, west
             const double *s0 = p.S + off;
-            constexpr int NPT = 4;  // nodes per thread per unrolled chunk
-            for (int ib = ilo + tid; ib <= ihi; ib += NPT * nthr) {
+            for (int ib = ilo + tid; ib <= ihi; ib += NB * nthr) {
                 const long long cb = ib - (ilo + tid);  // element distance of this chunk from the thread's first node
                 const double *up = up0 + cb, *dn = dn0 + cb, *sp = s0 + cb;
                 double *me = const_cast<double *>(me0) + cb;
                 const double2 *lvu = lvu0 + cb, *lhu = lhu0 + cb, *lvd = lvd0 + cb, *lhd = lhd0 + cb;
+                // request the operands of all NB nodes first; the stores follow all loads (for the compiler they alias)
+                double un[NB], uw[NB], us[NB], ue[NB], old[NB], sv[NB];
+                double2 ln[NB], lw[NB], ls[NB], le[NB];
 #pragma unroll
-                for (int e = 0; e < NPT; ++e) {
-                    if (ib + e * nthr > ihi) break;
+                for (int e = 0; e < NB; ++e) {
                     const int k = e * nthr;  // compile-time: immediate address offsets
-                    const double un = __ldcg(up + k - 1), uw = __ldcg(up + k);
-                    const double us = __ldcg(dn + k + 1), ue = __ldcg(dn + k);
-                    const double old = __ldcg(me + k);
-                    double2 ln = {1.0, 1.0}, ls = ln, lw = ln, le = ln;
-                    double sv = 0.0;
-                    if (HAS_NOISE) {
-                        ln = __ldg(lvu + k - 1);
-                        lw = __ldg(lhu + k);
-                        ls = __ldg(lvd + k);
-                        le = __ldg(lhd + k);
+                    ln[e] = lw[e] = ls[e] = le[e] = make_double2(1.0, 1.0);
+                    sv[e] = 0.0;
+                    if (ib + k <= ihi) {
+                        un[e] = __ldcg(up + k - 1);
+                        uw[e] = __ldcg(up + k);
+                        us[e] = __ldcg(dn + k + 1);
+                        ue[e] = __ldcg(dn + k);
+                        old[e] = __ldcg(me + k);
+                        if (HAS_NOISE) {
+                            ln[e] = __ldg(lvu + k - 1);
+                            lw[e] = __ldg(lhu + k);
+                            ls[e] = __ldg(lvd + k);
+                            le[e] = __ldg(lhd + k);
+                        }
+                        if (HAS_SRC) sv[e] = __ldg(sp + k);
                     }
-                    if (HAS_SRC) sv = __ldg(sp + k);
-                    const double nw = relax_node<HAS_NOISE, HAS_SRC>(un, us, uw, ue, ln, ls, lw, le, sv);
-                    mx = max_ignore_nan(mx, fabs(__dsub_rn(nw, old)));
-                    __stcg(me + k, nw);
+                }
+#pragma unroll
+                for (int e = 0; e < NB; ++e) {
+                    const int k = e * nthr;
+                    if (ib + k <= ihi) {
+                        const double nw = relax_node<HAS_NOISE, HAS_SRC>(un[e], us[e], uw[e], ue[e], ln[e], ls[e], lw[e], le[e], sv[e]);
+                        mx = max_ignore_nan(mx, fabs(__dsub_rn(nw, old[e])));
+                        __stcg(me + k, nw);
+                    }
                 }
             }
             // next diagonal: one pitch further, and one node further once the diagonal starts at the east column
@@ -660,10 +674,14 @@ struct RingCfg {
 
 template <bool N, bool S>
 static const void *ring_fn(int npt) {
-    switch (npt) {  // <= 0: generic kernel K2, the code is minus the block size
-        case -1024: return (const void *)exact_ring_kernel<N, S, 1024, 1>;
-        case -512: return (const void *)exact_ring_kernel<N, S, 512, 2>;
-        case -256: return (const void *)exact_ring_kernel<N, S, 256, 2>;
+    // <= 0: generic kernel K2, the code is minus the block size.  Measured at 4096^2 with links (B200, round 2): the
+    // 64-register shapes with one node in flight per thread (512 x 2 CTAs: 87 GLUP/s at K=1000; 1024 x 1: 58 at K=100)
+    // beat the 128-register shapes with four nodes in flight (256 x 2: 71; 512 x 1: 62 / 43) -- more warps hide the
+    // L2 latency better than more loads per warp; without links four nodes in flight fit 64 registers: 165 -> 205.
+    switch (npt) {
+        case -1024: return (const void *)exact_ring_kernel<N, S, 1024, 1, N ? 1 : 4>;
+        case -512: return (const void *)exact_ring_kernel<N, S, 512, 2, N ? 1 : 4>;
+        case -256: return (const void *)exact_ring_kernel<N, S, 256, 2, 4>;
         case 1: return (const void *)exact_ring2_kernel<N, S, 1>;
         case 2: return (const void *)exact_ring2_kernel<N, S, 2>;
         case 4: return (const void *)exact_ring2_kernel<N, S, 4>;
