@@ -818,7 +818,10 @@ static int solve_ring(double *grid, const double *nh, const double *nv, const do
     int64_t done = 0, result_iters = max_iter;
     while (done < max_iter) {
         const int64_t chunk = may_stop ? std::min<int64_t>(max_iter - done, chunk_cap) : (max_iter - done);
-        const int g = (int)std::min<int64_t>(chunk, gmax);
+        // CTAs: as many as fit, but balanced over the rounds (sweeps c, c+G, c+2G ... per CTA): 300 sweeps on 296 slots
+        // would run one full round plus a nearly serial round of 4; 2 rounds of 150 finish sooner
+        const int64_t rounds = (chunk + gmax - 1) / gmax;
+        const int g = (int)((chunk + rounds - 1) / rounds);
         if (may_stop) APDE_CUDA(cudaMemcpyAsync(snap.p, U.p, dbytes, cudaMemcpyDeviceToDevice, 0));
         APDE_CUDA(cudaMemsetAsync(d_prog.p, 0, d_prog.bytes, 0));
         p.hist = d_hist.as<double>() + done;
