@@ -250,7 +250,13 @@ class AnalogPDESolver:
 # DigitalSolver -- upstream solver.py:302-386
 # ----------------------------------------------------------------------------------------------
 class DigitalSolver:
-    """Finite-difference Gauss-Seidel for the same stencil, relaxed on the GPU."""
+    """Finite-difference Gauss-Seidel for the same stencil, relaxed on the GPU.
+
+    ``energy_joules()`` charges ``iterations_run`` sweeps like upstream (solver.py:381-386).  In the default
+    ``exact`` mode that count is the reference's; the red-black modes test convergence every ``APDE_CHECK_EVERY``
+    (32) sweeps, so their count -- and the digital energy derived from it -- is rounded up to the end of the check
+    interval (at most 31 sweeps more than the first crossing); ``multigrid`` counts cycles, not sweeps.
+    """
 
     backend_mode: Optional[str] = None
 

@@ -144,3 +144,24 @@ def test_bad_arguments_are_rejected_before_any_device_work():
         _backend.solve("exact", g, np.ones((4, 4)), None, None, 1e-6, 10)
     with pytest.raises(ValueError):
         _backend.solve("nonsense", g, None, None, None, 1e-6, 10)
+
+
+def test_degenerate_grid_raises_like_the_reference():
+    """A 1 x 1 grid divides by zero when the reference evaluates h = 1/(max(rows, cols) - 1) (solver.py:254, :329),
+    with or without a source; the mirror evaluates h first too.  No GPU is touched before the error."""
+    from analog_pde_solver import AnalogPDESolver, DigitalSolver
+    for solver in (AnalogPDESolver(rows=1, cols=1), DigitalSolver(rows=1, cols=1)):
+        with pytest.raises(ZeroDivisionError):
+            solver.solve(lambda i, j, r, c: 0.0)
+
+
+def test_environment_options_are_validated(monkeypatch):
+    """Malformed APDE_* values fail with a message naming the variable, not deep inside solve()."""
+    from analog_pde_solver import DigitalSolver
+    d = DigitalSolver(rows=8, cols=8)
+    for name, value in (("APDE_MODE", "fastest"), ("APDE_CHECK_EVERY", "often"), ("APDE_GPUS", "0"),
+                        ("APDE_EXACT_PATH", "diagonal"), ("APDE_OMEGA", "big")):
+        monkeypatch.setenv(name, value)
+        with pytest.raises(ValueError, match=name if name != "APDE_MODE" else "fastest"):
+            d.solve(lambda i, j, r, c: 1.0 if i == 0 else None, mode=None if name == "APDE_MODE" else "redblack")
+        monkeypatch.delenv(name)
