@@ -95,7 +95,7 @@ def load():
     lib.apde_solve_redblack_ex.argtypes = [ctypes.c_int, _dp, _dp, _dp, _dp] + solve_tail + [
         ctypes.c_int, ctypes.c_double, ctypes.c_int, _dp, _i64p, _dp]
     lib.apde_solve_multigrid.restype = ctypes.c_int
-    lib.apde_solve_multigrid.argtypes = [ctypes.c_int, _dp, _dp, _i64, _i64, ctypes.c_double, _i64, ctypes.c_int,
+    lib.apde_solve_multigrid.argtypes = [ctypes.c_int, _dp, _dp, _dp, _dp, _i64, _i64, ctypes.c_double, _i64, ctypes.c_int,
                                          ctypes.c_int, ctypes.c_int, _dp, _i64p, _dp]
     lib.apde_multigrid_levels.restype = ctypes.c_int
     lib.apde_multigrid_levels.argtypes = [_i64, _i64]
@@ -200,10 +200,8 @@ def _solve_once(lib, mode, grid, nh, nv, src, tol, max_iter, check_every, tempor
         rc = lib.apde_solve_exact_f64_path(*head, _ptr(hist), ctypes.byref(iters), ctypes.byref(ksec),
                                            EXACT_PATHS[exact_path])
     elif mode in ("multigrid", "multigrid32"):
-        if nh is not None or nv is not None:
-            raise ValueError("multigrid supports the ideal mesh only (no link mismatch); use redblack_kcl / redblack_sor")
         nu = int(os.environ.get("APDE_MG_SMOOTH", "0"))
-        rc = lib.apde_solve_multigrid(4 if mode == "multigrid32" else 8, _ptr(grid), _ptr(src), rows, cols, float(tol),
+        rc = lib.apde_solve_multigrid(4 if mode == "multigrid32" else 8, _ptr(grid), _ptr(nh), _ptr(nv), _ptr(src), rows, cols, float(tol),
                                       max_iter, nu, nu, int(os.environ.get("APDE_MG_COARSE_SWEEPS", "0")), _ptr(hist),
                                       ctypes.byref(iters), ctypes.byref(ksec))
     elif mode in EXTENDED_MODES:

@@ -22,8 +22,8 @@ variable ``APDE_MODE``; default ``"exact"``:
                     reference's update diverges with mismatch; a DIFFERENT (physically normalised) fixed point
                     when links are mismatched, the same one when they are ideal.  ``omega=`` applies too.
 
-* ``multigrid`` / ``multigrid32`` -- geometric V-cycles with the red-black kernel as smoother, ideal mesh only, any grid
-                    size: ``iterations_run`` counts CYCLES (each about 5 fine sweeps of work) and
+* ``multigrid`` / ``multigrid32`` -- geometric V-cycles with the red-black kernel as smoother, any grid size; with
+                    mismatched links it solves the normalised (``redblack_kcl``) system: ``iterations_run`` counts CYCLES (each about 5 fine sweeps of work) and
                     ``residual_history`` holds one entry per cycle (how far the cycle moved any node); ``max_iter``
                     caps the cycles.  16384 x 16384 Poisson reaches its discretisation error in 12 cycles.
 

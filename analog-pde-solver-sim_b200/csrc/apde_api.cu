@@ -156,18 +156,18 @@ int apde_solve_redblack_ex(int dtype_bytes, double *grid, const double *noise_h,
                           residual_history, iterations_run, kernel_seconds, omega, normalised != 0);
 }
 
-int apde_solve_multigrid(int dtype_bytes, double *grid, const double *source, int64_t rows, int64_t cols, double tol,
-                         int64_t max_cycles, int nu1, int nu2, int coarse_sweeps, double *residual_history,
-                         int64_t *cycles_run, double *kernel_seconds) {
-    APDE_TRY(check_solve_args("apde_solve_multigrid", grid, nullptr, nullptr, rows, cols, max_cycles, residual_history,
+int apde_solve_multigrid(int dtype_bytes, double *grid, const double *noise_h, const double *noise_v,
+                         const double *source, int64_t rows, int64_t cols, double tol, int64_t max_cycles, int nu1, int nu2,
+                         int coarse_sweeps, double *residual_history, int64_t *cycles_run, double *kernel_seconds) {
+    APDE_TRY(check_solve_args("apde_solve_multigrid", grid, noise_h, noise_v, rows, cols, max_cycles, residual_history,
                               cycles_run));
     if (dtype_bytes != 4 && dtype_bytes != 8) {
         set_error("apde_solve_multigrid: dtype_bytes must be 4 or 8");
         return APDE_EINVAL;
     }
     std::lock_guard<std::mutex> lock(g_solve_mutex);
-    return solve_multigrid(dtype_bytes, grid, source, rows, cols, tol, max_cycles, nu1, nu2, coarse_sweeps,
-                           residual_history, cycles_run, kernel_seconds);
+    return solve_multigrid(dtype_bytes, grid, noise_h, noise_v, source, rows, cols, tol, max_cycles, nu1, nu2,
+                           coarse_sweeps, residual_history, cycles_run, kernel_seconds);
 }
 
 int apde_multigrid_levels(int64_t rows, int64_t cols) { return rows >= 3 && cols >= 3 ? mg_level_count(rows, cols) : 1; }

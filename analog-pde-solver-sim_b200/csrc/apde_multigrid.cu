@@ -12,6 +12,12 @@
 // non-nested grid with ratio slightly above 2 (4096 -> 2048 -> 1024 ...); the transfers are hat-function weights
 // computed from the node positions, so every size works.  The coarsest level is relaxed by a fixed number of sweeps.
 //
+// Mismatched links (noise_h / noise_v given): the V-cycle then solves the NORMALISED system of the redblack_kcl mode,
+// sum_k g_k (u - u_k) = -src -- the reference's divide-by-4 system is indefinite at the sizes where multigrid matters.
+// Only the finest level carries the links (its smoother is the general per-colour kernel with the normalised update,
+// its residual uses the conductances); the coarse levels keep the ideal 5-point operator, which a 1 % mismatch
+// perturbs by 1 %: the coarse-grid correction stays accurate and the cycle count barely moves.
+//
 // Every level is an ordinary apde_plan (padded strip layout, plan dtype), so the smoother is literally
 // plan_run(); the two transfer kernels below work between plans.  All arithmetic is explicit round-to-nearest with a
 // fixed association, restated by the CPU checker of the tests, so cycles are bit-reproducible.
@@ -25,13 +31,26 @@
 
 namespace apde {
 
-// r_ij = ((((uN + uS) + uW) + uE) - 4 u) - src   at interior nodes, 0 on the ring
+// r_ij = ((((uN + uS) + uW) + uE) - 4 u) - src   at interior nodes, 0 on the ring.
+// With links (finest level of a mismatched mesh, Kirchhoff form):
+// r_ij = ((((gN*uN + gS*uS) + gW*uW) + gE*uE) - (((gN + gS) + gW) + gE) * u) - src
 template <typename T>
-__device__ __forceinline__ T mg_residual(const T *__restrict__ u, const T *__restrict__ src, long long c, long long pitch) {
-    T t = Ar<T>::add(u[c - pitch], u[c + pitch]);
-    t = Ar<T>::add(t, u[c - 1]);
-    t = Ar<T>::add(t, u[c + 1]);
-    t = Ar<T>::sub(t, Ar<T>::mul((T)4, u[c]));
+__device__ __forceinline__ T mg_residual(const T *__restrict__ u, const T *__restrict__ src, const T *__restrict__ gh,
+                                         const T *__restrict__ gv, long long c, long long pitch) {
+    T t;
+    if (gh) {
+        const T gn = gv[c - pitch], gs = gv[c], gw = gh[c - 1], ge = gh[c];
+        t = Ar<T>::add(Ar<T>::mul(gn, u[c - pitch]), Ar<T>::mul(gs, u[c + pitch]));
+        t = Ar<T>::add(t, Ar<T>::mul(gw, u[c - 1]));
+        t = Ar<T>::add(t, Ar<T>::mul(ge, u[c + 1]));
+        const T sg = Ar<T>::add(Ar<T>::add(Ar<T>::add(gn, gs), gw), ge);
+        t = Ar<T>::sub(t, Ar<T>::mul(sg, u[c]));
+    } else {
+        t = Ar<T>::add(u[c - pitch], u[c + pitch]);
+        t = Ar<T>::add(t, u[c - 1]);
+        t = Ar<T>::add(t, u[c + 1]);
+        t = Ar<T>::sub(t, Ar<T>::mul((T)4, u[c]));
+    }
     if (src) t = Ar<T>::sub(t, src[c]);
     return t;
 }
@@ -49,7 +68,8 @@ __device__ __forceinline__ double mg_hat(int f, int I, double inv_r) {
 
 // coarse source src_c(I,J) = -sum_f sum_g P[f][I] P[g][J] r(f,g); coarse u = 0 everywhere (zero initial error, zero ring)
 template <typename T>
-__global__ void mg_restrict_kernel(const T *__restrict__ uf, const T *__restrict__ sf, long long pitch_f, long long padl_f,
+__global__ void mg_restrict_kernel(const T *__restrict__ uf, const T *__restrict__ sf, const T *__restrict__ ghf,
+                                   const T *__restrict__ gvf, long long pitch_f, long long padl_f,
                                    int rows_f, int cols_f, T *__restrict__ uc0, T *__restrict__ uc1, T *__restrict__ sc,
                                    long long pitch_c, long long padl_c, int rows_c, int cols_c, double inv_rx, double inv_ry,
                                    double rx, double ry) {
@@ -71,7 +91,7 @@ __global__ void mg_restrict_kernel(const T *__restrict__ uf, const T *__restrict
                 for (int g = g0; g <= g1; ++g) {
                     const double wg = mg_hat(g, J, inv_ry);
                     if (wg == 0.0) continue;
-                    const double r = (double)mg_residual<T>(uf, sf, (long long)f * pitch_f + padl_f + g, pitch_f);
+                    const double r = (double)mg_residual<T>(uf, sf, ghf, gvf, (long long)f * pitch_f + padl_f + g, pitch_f);
                     row = __dadd_rn(row, __dmul_rn(wg, r));
                 }
                 acc = __dadd_rn(acc, __dmul_rn(wf, row));
@@ -121,7 +141,7 @@ template <typename T>
 int restrict_to(apde_plan *f, apde_plan *c) {
     const int tg = f->sm_count * 8;
     const double rx = (double)(f->d.grows - 1) / (double)(c->d.grows - 1), ry = (double)(f->d.cols - 1) / (double)(c->d.cols - 1);
-    mg_restrict_kernel<T><<<tg, 256>>>(f->U<T>(f->cur), f->S<T>(), f->pitch, f->padl, (int)f->d.grows, (int)f->d.cols,
+    mg_restrict_kernel<T><<<tg, 256>>>(f->U<T>(f->cur), f->S<T>(), f->GH<T>(), f->GV<T>(), f->pitch, f->padl, (int)f->d.grows, (int)f->d.cols,
                                        c->U<T>(0), c->U<T>(1), c->S<T>(), c->pitch, c->padl, (int)c->d.grows, (int)c->d.cols,
                                        1.0 / rx, 1.0 / ry, rx, ry);
     APDE_CUDA(cudaGetLastError());
@@ -168,8 +188,9 @@ int mg_level_count(int64_t rows, int64_t cols) {
 // max_change says little about convergence), or max_cycles.  hist[c] = an upper bound of cycle c's max change:
 // the sum of its fine-grid smoothing sweeps' max_change values and of max |coarse-grid correction|, accumulated in
 // fp64 in the order pre-smoothing sweeps, correction, post-smoothing sweeps.  *cycles = cycles run.
-int solve_multigrid(int elem, double *grid, const double *src, int64_t rows, int64_t cols, double tol,
-                    int64_t max_cycles, int nu1, int nu2, int coarse_sweeps, double *hist, int64_t *cycles, double *ksec) {
+int solve_multigrid(int elem, double *grid, const double *nh, const double *nv, const double *src, int64_t rows,
+                    int64_t cols, double tol, int64_t max_cycles, int nu1, int nu2, int coarse_sweeps, double *hist,
+                    int64_t *cycles, double *ksec) {
     if (ksec) *ksec = 0.0;
     if (max_cycles <= 0) {
         *cycles = max_cycles;
@@ -192,7 +213,7 @@ int solve_multigrid(int elem, double *grid, const double *src, int64_t rows, int
         auto L = std::make_unique<Level>();
         apde_plan_desc d{};
         d.dtype_bytes = elem;
-        d.has_noise = 0;
+        d.has_noise = (l == 0 && nh != nullptr) ? 1 : 0;  // links live on the finest level only (see the header)
         d.has_source = (l > 0 || src != nullptr) ? 1 : 0;
         d.temporal_depth = std::min(std::max(nu1, nu2), max_temporal_depth());
         d.grows = r;
@@ -207,7 +228,8 @@ int solve_multigrid(int elem, double *grid, const double *src, int64_t rows, int
         c = mg_coarse_size(c);
     }
     apde_plan *fine = lv[0]->plan;
-    APDE_TRY(plan_upload(fine, grid, nullptr, nullptr, src));
+    if (nh) fine->kcl = true;  // mismatched mesh: the normalised (Kirchhoff) update, smoothed by the general kernel
+    APDE_TRY(plan_upload(fine, grid, nh, nv, src));
     EventPair ev;
     APDE_TRY(ev.init());
     APDE_CUDA(cudaEventRecord(ev.a));

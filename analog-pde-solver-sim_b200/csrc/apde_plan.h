@@ -80,8 +80,9 @@ int solve_redblack(int elem, double *grid, const double *nh, const double *nv, c
 int plan_set_relaxation(apde_plan *p, double omega, int normalised);
 // implemented in apde_multigrid.cu
 int mg_level_count(int64_t rows, int64_t cols);
-int solve_multigrid(int elem, double *grid, const double *src, int64_t rows, int64_t cols, double tol,
-                    int64_t max_cycles, int nu1, int nu2, int coarse_sweeps, double *hist, int64_t *cycles, double *ksec);
+int solve_multigrid(int elem, double *grid, const double *nh, const double *nv, const double *src, int64_t rows,
+                    int64_t cols, double tol, int64_t max_cycles, int nu1, int nu2, int coarse_sweeps, double *hist,
+                    int64_t *cycles, double *ksec);
 // implemented in apde_exact.cu
 int selftest_division(int64_t n, uint64_t seed, int64_t *mismatches);
 int solve_exact_f64(double *grid, const double *nh, const double *nv, const double *src,

@@ -3,11 +3,12 @@
 (20 x 20, top edge hot: iterations, accuracy, energy model, ASCII heat-map, centre-column profile) at any size.
 
     python examples/laplace_heat_b200.py                                   # 20 x 20, exact (bit-identical) path
-    python examples/laplace_heat_b200.py --n 4097 --mode multigrid --tol 1e-9            # ideal mesh, 9 cycles
-    python examples/laplace_heat_b200.py --n 4096 --mode redblack_kcl --omega auto --max-iter 40000   # with mismatch
+    python examples/laplace_heat_b200.py --n 4096 --mode multigrid --tol 1e-9            # ~12 cycles per solve
+    python examples/laplace_heat_b200.py --n 4096 --mode redblack_kcl --omega auto --max-iter 40000
 
-With 1 % mismatch the reference's update diverges beyond N ~ 200 (SURVEY finding 2); --mode redblack_kcl is the
-normalised update that converges at every size.  Large grids are shown block-averaged.
+With 1 % mismatch the reference's update diverges beyond N ~ 200 (SURVEY finding 2); --mode redblack_kcl and
+--mode multigrid use the normalised (Kirchhoff) update, which converges at every size.  Large grids are shown
+block-averaged.
 """
 import argparse
 import os
@@ -43,8 +44,6 @@ runs = [("analog, ideal", AnalogPDESolver(rows=n, cols=n, noise_level=0.0, rng_s
 sol = {}
 for name, s in runs:
     mode = a.mode
-    if mode.startswith("multigrid") and "mismatch" in name:
-        mode = "redblack_kcl" + ("32" if mode.endswith("32") else "")   # the V-cycle is for the ideal mesh
     kw = {"omega": omega} if (omega is not None and ("sor" in mode or "kcl" in mode)) else {}
     if mode.startswith("redblack_kcl") and "mismatch" in name and not kw:
         kw = {"omega": _backend.optimal_omega(n, n)}

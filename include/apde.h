@@ -111,8 +111,10 @@ int apde_solve_redblack_ex(int dtype_bytes, double *grid, const double *noise_h,
                            int64_t *iterations_run, double *kernel_seconds);
 
 /* ------------------------------------------------------------------------------------------
- * MULTIGRID (not in the reference) -- geometric V(nu1, nu2) cycles for the ideal mesh
- * (no link mismatch: DigitalSolver, or AnalogPDESolver with noise_level 0), the fused red-black kernels as smoother,
+ * MULTIGRID (not in the reference) -- geometric V(nu1, nu2) cycles.  Ideal mesh (noise_h ==
+ * noise_v == NULL: DigitalSolver, or AnalogPDESolver with noise_level 0): the reference's system, the fused red-black
+ * kernels as smoother.  Mismatched links: the NORMALISED (Kirchhoff) system of apde_solve_redblack_ex(normalised = 1) --
+ * the links act on the finest level (general kernel as smoother), the coarse levels keep the ideal operator.  Either way:
  * restriction = transpose of the (bi)linear prolongation, rediscretised 5-point operator on every level.  A level of n
  * nodes per side coarsens to (n+1)/2 uniform nodes over the same length while both sides keep >= 3 nodes: nested
  * (every second node) for 2^k+1-like sides, otherwise non-nested with a spacing ratio slightly above 2 (4096 -> 2048),
@@ -124,9 +126,9 @@ int apde_solve_redblack_ex(int dtype_bytes, double *grid, const double *noise_h,
  * criterion, solver.py:283, applied to a whole cycle -- one smoothing sweep barely moves a smooth error on a fine grid,
  * so a per-sweep test would stop far too early) or after max_cycles; *cycles_run is the number of cycles.  nu1 / nu2 / coarse_sweeps <= 0 select 2 / 2 / 32.
  * ---------------------------------------------------------------------------------------- */
-int apde_solve_multigrid(int dtype_bytes, double *grid, const double *source, int64_t rows, int64_t cols, double tol,
-                         int64_t max_cycles, int nu1, int nu2, int coarse_sweeps, double *residual_history,
-                         int64_t *cycles_run, double *kernel_seconds);
+int apde_solve_multigrid(int dtype_bytes, double *grid, const double *noise_h, const double *noise_v,
+                         const double *source, int64_t rows, int64_t cols, double tol, int64_t max_cycles, int nu1, int nu2,
+                         int coarse_sweeps, double *residual_history, int64_t *cycles_run, double *kernel_seconds);
 int apde_multigrid_levels(int64_t rows, int64_t cols);
 
 /* The fused depth the one-shot solves use for temporal_depth <= 0 (dtype_bytes 8 / 4, with or without mismatch). */

@@ -190,7 +190,7 @@ def _mg_hat_matrix(n_fine, n_coarse):
 
 
 def multigrid(grid, source=None, tol: float = 1e-8, max_cycles: int = 50, nu1: int = 2, nu2: int = 2,
-              coarse_sweeps: int = 32, dtype=np.float64):
+              coarse_sweeps: int = 32, dtype=np.float64, noise_h=None, noise_v=None):
     """CPU statement of csrc/apde_multigrid.cu (NOT in the reference): V(nu1, nu2) cycles on the ideal mesh,
     red-black smoothing (red_black above), r = ((((uN+uS)+uW)+uE) - 4u) - src, levels of ((n+1)//2) nodes per side,
     hat-function transfer weights from the node positions (restriction = transpose of linear interpolation, sums over
@@ -205,17 +205,32 @@ def multigrid(grid, source=None, tol: float = 1e-8, max_cycles: int = 50, nu1: i
     src = None if source is None else np.asarray(source, dtype=np.float64).astype(dtype)
     L = _mg_levels(rows, cols)
     four = dt(4)
+    gh = gv = None
+    if noise_h is not None:   # links act on the finest level only: normalised (Kirchhoff) update and residual there
+        gh = reciprocal_links(np.asarray(noise_h, dtype=np.float64), dtype)
+        gv = reciprocal_links(np.asarray(noise_v, dtype=np.float64), dtype)
 
-    def smooth(uu, ss, n):
-        out, h, _ = red_black(uu.astype(np.float64), None, None, None if ss is None else ss.astype(np.float64), n, dtype=dtype)
+    def smooth(uu, ss, n, fine=False):
+        if fine and gh is not None:
+            out, h, _ = red_black(uu.astype(np.float64), None, None, None if ss is None else ss.astype(np.float64), n,
+                                  dtype=dtype, conductances=(gh, gv), kcl=True)
+        else:
+            out, h, _ = red_black(uu.astype(np.float64), None, None, None if ss is None else ss.astype(np.float64), n, dtype=dtype)
         return out, h
 
-    def restrict(uu, ss):
+    def restrict(uu, ss, fine=False):
         r = np.zeros(uu.shape, dtype=np.float64)
-        t = (uu[:-2, 1:-1] + uu[2:, 1:-1])
-        t = t + uu[1:-1, :-2]
-        t = t + uu[1:-1, 2:]
-        t = t - four * uu[1:-1, 1:-1]
+        if fine and gh is not None:
+            gn, gs_, gw, ge = gv[:-1, 1:-1], gv[1:, 1:-1], gh[1:-1, :-1], gh[1:-1, 1:]
+            t = gn * uu[:-2, 1:-1] + gs_ * uu[2:, 1:-1]
+            t = t + gw * uu[1:-1, :-2]
+            t = t + ge * uu[1:-1, 2:]
+            t = t - (((gn + gs_) + gw) + ge) * uu[1:-1, 1:-1]
+        else:
+            t = (uu[:-2, 1:-1] + uu[2:, 1:-1])
+            t = t + uu[1:-1, :-2]
+            t = t + uu[1:-1, 2:]
+            t = t - four * uu[1:-1, 1:-1]
         if ss is not None:
             t = t - ss[1:-1, 1:-1]
         r[1:-1, 1:-1] = t.astype(np.float64)
@@ -263,18 +278,18 @@ def multigrid(grid, source=None, tol: float = 1e-8, max_cycles: int = 50, nu1: i
         pre = post = np.zeros(0)
         corr = []
         for l in range(L - 1):
-            us[l], h = smooth(us[l], ss[l], nu1)
+            us[l], h = smooth(us[l], ss[l], nu1, fine=(l == 0))
             if l == 0:
                 pre = h
-            sc = restrict(us[l], ss[l])
+            sc = restrict(us[l], ss[l], fine=(l == 0))
             us.append(np.zeros_like(sc))
             ss.append(sc)
-        us[L - 1], h = smooth(us[L - 1], ss[L - 1], coarse_sweeps if L > 1 else nu1 + nu2)
+        us[L - 1], h = smooth(us[L - 1], ss[L - 1], coarse_sweeps if L > 1 else nu1 + nu2, fine=(L == 1))
         if L == 1:
             pre, post = h[:nu1], h[nu1:]
         for l in range(L - 2, -1, -1):
             us[l] = prolong(us[l], us[l + 1], corr if l == 0 else None)
-            us[l], h = smooth(us[l], ss[l], nu2)
+            us[l], h = smooth(us[l], ss[l], nu2, fine=(l == 0))
             if l == 0:
                 post = h
         u = us[0]
