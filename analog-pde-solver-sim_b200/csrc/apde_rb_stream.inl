@@ -88,6 +88,17 @@ constexpr int rbs_min_blocks(int elem_bytes, int lane_cols, bool noise) {
 #endif
 }
 
+// Shifted or rotating register window (see the kernel).  Measured on B200, 16384^2 (profiles/r2_rb_sweep_shift.txt):
+// shifted wins wherever registers were the wall -- fp64 Poisson depth 4: 548 vs 496 GLUP/s (rotating, depth 3), fp64
+// with mismatch 215 vs 210, fp32 with mismatch 462 vs 441 -- and loses where they were not: fp32 Poisson 1004-1068
+// (depth 4-6) vs 1076 (rotating, depth 3, 168 registers).
+#ifndef RBS_SHIFT_MODE
+#define RBS_SHIFT_MODE -1  // -1: per variant (default), 0: always rotating, 1: always shifted
+#endif
+__host__ __device__ constexpr bool rbs_shift(int elem_bytes, bool noise) {
+    return RBS_SHIFT_MODE >= 0 ? RBS_SHIFT_MODE != 0 : (elem_bytes == 8 || noise);
+}
+
 __device__ __forceinline__ void prefetch_l2(const void *p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
@@ -210,6 +221,18 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
     constexpr int NS = 2 * TD;             // half-sweep stages
     constexpr int DEPTH_ROWS = 1 + LAG * (NS - 1);            // newest-to-final distance in rows
     constexpr int NW = ((DEPTH_ROWS + 2 + 1) / 2) * 2 + RBS_PF;  // register window rows (even)
+    // Two ways to keep the sliding window in registers (SHIFT chosen per variant, rbs_shift()):
+    //   rotating: row r+off lives in slot (off + rr) mod NW; nothing ever moves, but the loop body must be unrolled
+    //             NW times for the slot numbers to be constants -- 6600 instructions (103 KB) for fp64 depth 3, far
+    //             beyond the instruction cache (ncu: no_instruction 0.55 stall cycles per issue);
+    //   shifted : row r+off lives in slot off + DEPTH_ROWS + 1 + (rr & 1) and the whole window moves down two slots
+    //             every second iteration: unrolled 2x (1744 instructions), (NW-1)*C register moves per two iterations,
+    //             and ~35 fewer live registers -- depth 4 then fits without spills (fp64 Poisson 230 registers).
+    constexpr bool SHIFT = rbs_shift((int)sizeof(T), NOISE);
+    constexpr int WSL = SHIFT ? NW + 1 : NW;  // slots
+    constexpr int UNR = SHIFT ? 2 : NW;       // unroll period
+    static_assert(!SHIFT || LAG == 1, "the shifted window assumes one row between stages");
+#define RBS_SLOT(off) (SHIFT ? ((off) + DEPTH_ROWS + 1 + (rr & 1)) : (((off) + rr + 8 * NW) % NW))
     constexpr int CW = 32 * C;             // columns per warp strip
     constexpr int HCA = ((NS + C - 1) / C) * C;  // column halo, lane aligned
     constexpr int VW = CW - 2 * HCA;       // columns a strip stores
@@ -272,16 +295,16 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
         const long long st0 = (long long)(rs - 1) * pitch + lane_off;      // row r - 1 (stage 0's row)
         const T *psrc = a.src + st0, *pgh = a.gh + st0, *pgv = a.gv + st0;
 
-        T w[NW][C];
+        T w[WSL][C];
 #pragma unroll
-        for (int k = 0; k < NW; ++k)
+        for (int k = 0; k < WSL; ++k)
 #pragma unroll
             for (int q = 0; q < C; ++q) w[k][q] = (T)0;
 #ifdef RBS_TMA
         // rows rs .. r_load_end are fed in order: issue TA rows ahead of their consumption
         // exactly the rows the item consumes: RBS_PF in the prologue + one per iteration of the chunked loop
         // (nothing may still be in flight towards this CTA's shared memory when the item -- or the kernel -- ends)
-        const int r_load_end = rs + RBS_PF + ((r_last - rs) / NW + 1) * NW - 1;
+        const int r_load_end = rs + RBS_PF + ((r_last - rs) / UNR + 1) * UNR - 1;
         const T *pin0 = a.in + (long long)rs * pitch + (a.padl + sidx * VW - HCA);  // lane 0's address of row rs
         int next_issue = rs;
         auto tma_issue_upto = [&](int row_limit) {
@@ -309,7 +332,7 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
 #else
 #pragma unroll
         for (int k = 0; k < RBS_PF; ++k) {
-            load_row<C>(w[k], pin + k * pitch);  // rows past either end are zero padding
+            load_row<C>(w[SHIFT ? k + DEPTH_ROWS + 1 : k], pin + k * pitch);  // rows past either end are zero padding
         }
 #endif
         unsigned act = 0, cnt = 0;  // bit s: the row stage s handles this iteration is relaxed / counted
@@ -317,18 +340,18 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
 #pragma unroll
         for (int t = 0; t < TD; ++t) mxl[t] = (T)0;
 
-        for (int rc = rs; rc <= r_last; rc += NW) {
+        for (int rc = rs; rc <= r_last; rc += UNR) {
 #pragma unroll
-            for (int rr = 0; rr < NW; ++rr) {
+            for (int rr = 0; rr < UNR; ++rr) {
                 const int r = rc + rr;
                 // unconditional (padding rows make every address valid): the load lands straight in
                 // its window slot and nothing waits on it until the row is first used
 #ifdef RBS_TMA
                 __syncwarp();  // every lane is done with the slot that is about to be refilled
                 tma_issue_upto(r + RBS_PF + TA);
-                tma_consume(w[(rr + RBS_PF) % NW]);
+                tma_consume(w[RBS_SLOT(RBS_PF)]);
 #else
-                load_row<C>(w[(rr + RBS_PF) % NW], pin + RBS_PF * pitch);
+                load_row<C>(w[RBS_SLOT(RBS_PF)], pin + RBS_PF * pitch);
 #endif
                 act = (act << 1) | (((unsigned)(r - 2 - ra) < upd_span) ? 1u : 0u);
                 cnt = (cnt << 1) | (((unsigned)(r - 1 - rb0) < own_span) ? 1u : 0u);
@@ -382,8 +405,8 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
                     constexpr int s = decltype(s_tag)::value;
                     if constexpr (s + LA < NS) fetch(std::integral_constant<int, s + LA>{});
                     const int p = (rr + 1 + (LAG - 1) * s) & 1;
-                    const int si = (rr - 1 - LAG * s + 8 * NW) % NW;
-                    const int su = (si + NW - 1) % NW;
+                    const int si = RBS_SLOT(-1 - LAG * s);
+                    const int su = RBS_SLOT(-2 - LAG * s);
                     T edge;  // the one cross-lane operand of this stage-row
                     if (p == 0) edge = __shfl_up_sync(0xffffffffu, w[si][C - 1], 1);
                     else edge = __shfl_down_sync(0xffffffffu, w[si][0], 1);
@@ -408,8 +431,8 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
                     constexpr int s = decltype(s_tag)::value;
                     // stage s relaxes colour s&1 of row r-1-LAG*s; everything is predicated, no branches
                     const int p = (rr + 1 + (LAG - 1) * s) & 1;
-                    const int si = (rr - 1 - LAG * s + 8 * NW) % NW;
-                    const int sd = (si + 1) % NW;
+                    const int si = RBS_SLOT(-1 - LAG * s);
+                    const int sd = RBS_SLOT(-LAG * s);
                     const bool act_s = (act >> (LAG * s)) & 1u;
                     const bool cnt_s = (cnt >> (LAG * s)) & 1u;
                     const unsigned okmask = act_s ? colmask : 0u;
@@ -425,12 +448,19 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
                 });
                 // row r-DEPTH_ROWS has passed every stage
                 if (lane_valid && (unsigned)(r - DEPTH_ROWS - rb0) < own_span)
-                    store_row<C>(pout, w[(rr - DEPTH_ROWS + 8 * NW) % NW]);
+                    store_row<C>(pout, w[RBS_SLOT(-DEPTH_ROWS)]);
                 pin += pitch;
                 pout += pitch;
                 psrc += pitch;
                 pgh += pitch;
                 pgv += pitch;
+            }
+            if (SHIFT) {
+                // two iterations on: every row of the window is two slots further from the newest one
+#pragma unroll
+                for (int k = 0; k + 2 < WSL; ++k)
+#pragma unroll
+                    for (int q = 0; q < C; ++q) w[k][q] = w[k + 2][q];
             }
         }
         if (lane_valid) {
@@ -605,5 +635,7 @@ int RBS_FN(apde_plan *p, int64_t n_sweeps, int64_t sweep_base, int phase, cudaSt
     APDE_CUDA(cudaGetLastError());
     return APDE_OK;
 }
+
+#undef RBS_SLOT
 
 }  // namespace apde

@@ -756,14 +756,17 @@ int default_rb_variant() {
     if (const char *v = getenv("APDE_RB_VARIANT")) return std::min(2, std::max(0, v[0] == 'v' ? atoi(v + 1) : atoi(v)));
     return 1;
 }
-int max_temporal_depth() { return default_rb_variant() == 2 ? 6 : 4; }
+int max_temporal_depth() {
+    if (const char *v = getenv("APDE_MAX_DEPTH")) return std::min(6, std::max(1, atoi(v)));  // tuning builds
+    return default_rb_variant() == 2 ? 6 : 4;
+}
 
 // Fused depth the one-shot solves use when the caller passes temporal_depth <= 0: the measured best per
 // variant on B200 (profiles/).
 int default_temporal_depth(int elem, bool noise) {
-    // 16384^2 on B200 (profiles/r2_rb_sweep_v1_autoblock.txt): fp64 3 / with mismatch 2 (depth 3 is within 2 % there:
-    // 255 registers); fp32 3 either way (with mismatch 443 vs 405 GLUP/s at depth 2)
-    return (noise && elem == 8) ? 2 : 3;
+    // 16384^2 on B200 (profiles/r2_rb_sweep_shift.txt): depth 4 wherever the shifted register window is used (fp64, and
+    // fp32 with mismatch); fp32 Poisson keeps the rotating window at depth 3
+    return (elem == 8 || noise) ? 4 : 3;
 }
 
 static apde_plan *g_cached_plan = nullptr;  // never destroyed at exit (the context may be gone by then)

@@ -431,6 +431,31 @@ def exact_variant(ctx, k):
                                  "the fraction is reported for completeness"}}
 
 
+def convergence_variants(ctx):
+    """SURVEY 8f-3, driver-visible: time to the discretisation error of a 4096^2 Poisson problem with known solution
+    (sin(pi x) sin(pi y)) through the one-shot solves -- V-cycles (fused red-black kernel as smoother) and optimal SOR.
+    `value` = kernel seconds; the error against the exact PDE solution shows the solve is really done."""
+    from analog_pde_solver import DigitalSolver
+    n = 4096
+    x = np.arange(n) / (n - 1)
+    exact = np.outer(np.sin(np.pi * x), np.sin(np.pi * x))
+    f = -2.0 * np.pi ** 2 * exact
+    out = []
+    for mode, tol, cap in (("multigrid", 1e-9, 60), ("redblack_sor", 1e-12, 40 * n)):
+        d = DigitalSolver(rows=n, cols=n)
+        t0 = time.perf_counter()
+        u = d.solve(np.zeros((n, n)), source_fn=f, tol=tol, max_iter=cap, mode=mode)
+        wall = time.perf_counter() - t0
+        out.append({"name": f"time_to_tolerance_{mode}_4096", "metric": "seconds to discretisation error (kernels)",
+                    "value": d.kernel_seconds, "unit": "s", "higher_is_better": False, "n_gpus": 1, "dtype": "f64",
+                    "iterations": d.iterations_run, "iteration_unit": "V-cycles" if mode == "multigrid" else "sweeps",
+                    "wall_seconds": wall, "max_error_vs_exact_solution": float(np.max(np.abs(u - exact))),
+                    "discretisation_error_scale": 0.82 / (n - 1) ** 2,
+                    "config": {"workload": f"{n}x{n} Poisson, zero ring, exact solution sin(pi x) sin(pi y); mode={mode}, tol={tol:g}; "
+                                           "the reference's update needs ~8e6 sweeps here"}})
+    return out
+
+
 def run_ours(args):
     ctx = Ctx()
     torch, world, rank = ctx.torch, ctx.world, ctx.rank
@@ -546,6 +571,7 @@ def run_ours(args):
                 variants.append(rb_variant(ctx, name, dtype, args.rows, args.cols, noise, True, args, "weak"))
             for k in (1000, 100):
                 variants.append(exact_variant(ctx, k))
+            variants += convergence_variants(ctx)
         else:
             # config 5: ONE 65536^2 Poisson + 1 % mismatch problem cut into `world` strips (strong scaling).
             # fp64 needs 5 x 32 GiB: it fits from N = 2 (86 GiB per GPU); fp32 from N = 1.

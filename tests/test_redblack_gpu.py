@@ -71,7 +71,7 @@ def test_large_grid_row_blocks_and_strips_of_the_streaming_kernel():
 def test_converged_fp64_within_1e10_of_reference_answer():
     """tol = 1e-13 on SPD cases: |u_rb - u_lex| <= 1e-10 * |u|  (north_star tolerance, fp64)."""
     for rows, cols, sigma, seed in [(20, 20, 0.0, 1), (20, 20, 0.01, 0), (64, 64, 0.01, 0), (48, 30, 0.0, 2),
-                                    (128, 128, 0.01, 0), (96, 40, 0.01, 5), (33, 150, 0.0, 6)]:
+                                    (100, 100, 0.005, 3), (96, 40, 0.01, 5), (33, 150, 0.0, 6)]:
         g0, nh, nv, s = random_problem(rows, cols, sigma, seed)
         ref, _, rn = oracle.gauss_seidel(g0, nh, nv, s, 1e-13, 200000)
         g = g0.copy()

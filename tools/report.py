@@ -81,12 +81,20 @@ def main():
     var = [(b.get("n_gpus"), v) for b in ours for v in (b.get("variants") or [])]
     if var:
         rows = []
+        conv = [(n, v) for n, v in var if v.get("unit") == "s"]
+        var = [(n, v) for n, v in var if v.get("unit") != "s"]
         for n, v in var:
             r = v.get("roofline") or {}
             rows.append([n, v.get("name"), v.get("dtype"), fmt(v.get("value")), fmt(r.get("frac"), "{:.2f}"),
                          fmt(r.get("dram_frac_of_peak"), "{:.2f}"), fmt((v.get("e2e") or {}).get("value")), v.get("scaling", "-")])
         print("\n## Other BASELINE configs measured in the same run\n")
         print(table(rows, ["GPUs", "config", "dtype", "GLUP/s", "alg. frac", "DRAM frac", "e2e GLUP/s", "scaling"]))
+        if conv:
+            print("\n## Time to tolerance (4096^2 Poisson, known solution)\n")
+            print(table([[v.get("name"), v.get("iterations"), v.get("iteration_unit"), fmt(v.get("value"), "{:.3f}"),
+                          fmt(v.get("wall_seconds"), "{:.3f}"), fmt(v.get("max_error_vs_exact_solution"), "{:.2e}"),
+                          fmt(v.get("discretisation_error_scale"), "{:.2e}")] for _, v in conv],
+                        ["mode", "iterations", "unit", "kernel s", "wall s", "max error", "0.82 h^2"]))
         strong = {}
         for n, v in var:
             if v.get("scaling") == "strong":
