@@ -239,7 +239,10 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
     static_assert(VW > 0 && NW % 2 == 0, "bad tile");
     // prefetch distances, measured per variant on B200 (tools/rb_sweep.py): with conductances the extra
     // prefetch instructions cost more than they hide
-    constexpr int L2PF = NOISE ? 0 : L2PF_ROWS;
+#ifndef RBS_NOISE_L2PF
+#define RBS_NOISE_L2PF 0
+#endif
+    constexpr int L2PF = NOISE ? RBS_NOISE_L2PF : L2PF_ROWS;
     constexpr int OPF = NOISE ? RBS_OPF : 2 * RBS_OPF;
 
     if (a.stop && *a.stop) return;  // device-side stop: a sweep after the converged check interval is a no-op
@@ -379,7 +382,10 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
                 constexpr int CH = (C + 1) / 2;
                 // operands of the first LA stages are fetched up front, the rest one stage ahead
                 // (all of them when only the source is read; conductances would cost too many registers)
-                constexpr int LA = NOISE ? 1 : NS;
+#ifndef RBS_NOISE_LA
+#define RBS_NOISE_LA 1
+#endif
+                constexpr int LA = NOISE ? RBS_NOISE_LA : NS;
                 T o_sv[NS][CH], o_gn[NOISE ? NS : 1][CH], o_gs[NOISE ? NS : 1][CH], o_gw[NOISE ? NS : 1][CH], o_ge[NOISE ? NS : 1][CH];
                 auto fetch = [&](auto s_tag) {
                     constexpr int s = decltype(s_tag)::value;
