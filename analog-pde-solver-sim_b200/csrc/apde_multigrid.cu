@@ -146,6 +146,7 @@ int restrict_to(apde_plan *f, apde_plan *c) {
                                        1.0 / rx, 1.0 / ry, rx, ry);
     APDE_CUDA(cudaGetLastError());
     c->cur = 0;
+    c->split_dirty = true;  // the coarse source was rewritten
     c->pass_open = false;
     c->filled = true;
     f->launches++;

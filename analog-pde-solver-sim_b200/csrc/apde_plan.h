@@ -18,6 +18,11 @@ struct apde_plan {
     // buffers (all lrows x pitch, plan dtype) --------------------------------------------------
     apde::DevBuf u[2];        // ping-pong grids; u[cur] is current
     apde::DevBuf src, gh, gv; // source, 1/noise_h, 1/noise_v  (gh[i][j]: link (i,j)-(i,j+1); gv[i][j]: (i,j)-(i+1,j))
+    // colour-split copies of the three operand planes for the streaming kernel: within every row the even padded
+    // columns come first, then (half a pitch on) the odd ones, so the operands of one colour of a row are contiguous
+    // (a warp's operand load touches 2-3 L1 lines instead of 4-8).  Rebuilt from src/gh/gv when split_dirty.
+    apde::DevBuf src_cs, gh_cs, gv_cs;
+    bool split_dirty = true;
     apde::DevBuf resid;       // per-sweep max_change, plan dtype
     apde::DevBuf scratch;     // checksum outputs etc.
     apde::DevBuf stage;       // float64 staging for host<->device conversion (grown on demand, reused)
@@ -48,6 +53,9 @@ struct apde_plan {
     template <typename T> T *S() const { return src.p ? src.as<T>() + rowpad * pitch : nullptr; }
     template <typename T> T *GH() const { return gh.p ? gh.as<T>() + rowpad * pitch : nullptr; }
     template <typename T> T *GV() const { return gv.p ? gv.as<T>() + rowpad * pitch : nullptr; }
+    template <typename T> T *SC() const { return src_cs.p ? src_cs.as<T>() + rowpad * pitch : nullptr; }
+    template <typename T> T *GHC() const { return gh_cs.p ? gh_cs.as<T>() + rowpad * pitch : nullptr; }
+    template <typename T> T *GVC() const { return gv_cs.p ? gv_cs.as<T>() + rowpad * pitch : nullptr; }
 };
 
 namespace apde {
@@ -66,6 +74,7 @@ int plan_read_residuals(apde_plan *p, int64_t first, int64_t count, double *out,
 int plan_energy_sums(apde_plan *p, double *sum_h2, double *sum_v2, cudaStream_t st);
 int plan_checksum(apde_plan *p, double *sum_out, double *absmax_out, uint64_t *bits_out, cudaStream_t st);
 int plan_ensure_resid(apde_plan *p, int64_t cap);
+int plan_refresh_split(apde_plan *p, cudaStream_t st);
 void release_cached_plan();
 int default_temporal_depth(int elem, bool noise);
 int default_rb_variant();

@@ -48,7 +48,7 @@ constexpr int LAG = RBS_LAG;
 struct StreamArgs {
     const T *in;
     T *out;
-    const T *src, *gh, *gv;
+    const T *src, *gh, *gv;  // colour-split operand planes (apde_plan.h): even columns, then odd columns half a pitch on
     T *resid;  // slot of the first sweep of this pass
     const int *stop;  // optional device flag: set => the solve has converged, do nothing
     long long pitch, padl, lrows, cols, grows, row0;
@@ -84,6 +84,10 @@ constexpr int rbs_min_blocks(int elem_bytes, int lane_cols, bool noise) {
 #elif defined(RBS_F32_MINBLOCKS)
     return (elem_bytes == 4 && lane_cols == 4 && !noise) ? RBS_F32_MINBLOCKS : 1;
 #else
+#ifndef RBS_F64N_MINBLOCKS
+#define RBS_F64N_MINBLOCKS 1
+#endif
+    if (elem_bytes == 8 && lane_cols == 2 && noise) return RBS_F64N_MINBLOCKS;
     return (elem_bytes == 4 && lane_cols == 4 && !noise) ? 3 : 1;
 #endif
 }
@@ -97,6 +101,15 @@ constexpr int rbs_min_blocks(int elem_bytes, int lane_cols, bool noise) {
 #endif
 __host__ __device__ constexpr bool rbs_shift(int elem_bytes, bool noise) {
     return RBS_SHIFT_MODE >= 0 ? RBS_SHIFT_MODE != 0 : (elem_bytes == 8 || noise);
+}
+
+// Operand planes read by the kernel: colour-split copies (apde_plan.h) or the natural ones.  Split wins wherever it was
+// measured except fp32 Poisson, whose 168-register variant spills with the vector operand loads (887 vs 1040 GLUP/s).
+#ifndef RBS_SPLIT_MODE
+#define RBS_SPLIT_MODE -1  // -1: per variant (default), 0: natural everywhere, 1: split everywhere
+#endif
+__host__ __device__ constexpr bool rbs_split(int elem_bytes, bool noise) {
+    return RBS_SPLIT_MODE >= 0 ? RBS_SPLIT_MODE != 0 : (elem_bytes == 8 || noise);
 }
 
 __device__ __forceinline__ void prefetch_l2(const void *p) {
@@ -201,6 +214,24 @@ __device__ __forceinline__ float ld_operand(const float *p) {
 #endif
 }
 
+// N consecutive operands of one colour (colour-split planes).  ALIGNED: p is aligned to N elements -> one vector load.
+__device__ __forceinline__ void ld_operand_vec2(double *o, const double *p) {
+    asm("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(o[0]), "=d"(o[1]) : "l"(p));
+}
+__device__ __forceinline__ void ld_operand_vec2(float *o, const float *p) {
+    asm("ld.global.nc.v2.f32 {%0,%1}, [%2];" : "=f"(o[0]), "=f"(o[1]) : "l"(p));
+}
+template <int N, bool ALIGNED>
+__device__ __forceinline__ void ld_operands(T *o, const T *p) {
+    if constexpr (ALIGNED && N % 2 == 0) {
+#pragma unroll
+        for (int k = 0; k < N; k += 2) ld_operand_vec2(&o[k], p + k);
+    } else {
+#pragma unroll
+        for (int k = 0; k < N; ++k) o[k] = ld_operand(p + k);
+    }
+}
+
 template <int C>
 __device__ __forceinline__ void load_row(T (&w)[C], const T *p) {
     constexpr int PER = 16 / (int)sizeof(T);
@@ -232,6 +263,11 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
     constexpr int WSL = SHIFT ? NW + 1 : NW;  // slots
     constexpr int UNR = SHIFT ? 2 : NW;       // unroll period
     static_assert(!SHIFT || LAG == 1, "the shifted window assumes one row between stages");
+#ifndef RBS_FT
+#define RBS_FT 0
+#endif
+    constexpr bool SPLIT = rbs_split((int)sizeof(T), NOISE);
+    constexpr bool FT = RBS_FT && SHIFT && NOISE && SPLIT;
 #define RBS_SLOT(off) (SHIFT ? ((off) + DEPTH_ROWS + 1 + (rr & 1)) : (((off) + rr + 8 * NW) % NW))
     constexpr int CW = 32 * C;             // columns per warp strip
     constexpr int HCA = ((NS + C - 1) / C) * C;  // column halo, lane aligned
@@ -249,7 +285,7 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
     const int lane = threadIdx.x & 31;
     const long long warp_id = (long long)blockIdx.x * (RBS_THREADS / 32) + (threadIdx.x >> 5);
     const long long n_warps = (long long)gridDim.x * (RBS_THREADS / 32);
-    const long long pitch = a.pitch;
+    const long long pitch = a.pitch, half = a.pitch >> 1;
 
     T mx[TD];
 #pragma unroll
@@ -295,8 +331,19 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
         const long long lane_off = a.padl + jl0;
         const T *pin = a.in + (long long)rs * pitch + lane_off;            // row r
         T *pout = a.out + (long long)(rs - DEPTH_ROWS) * pitch + lane_off; // row r - DEPTH_ROWS
-        const long long st0 = (long long)(rs - 1) * pitch + lane_off;      // row r - 1 (stage 0's row)
+        // operands: row r - 1 (stage 0's row) of the colour-split planes, at the lane's first column pair
+        const long long st0 = (long long)(rs - 1) * pitch + (SPLIT ? ((a.padl + jl0) >> 1) : lane_off);
         const T *psrc = a.src + st0, *pgh = a.gh + st0, *pgv = a.gv + st0;
+#ifdef RBS_PF_FEW_LANES
+        // one prefetch per 128-byte line instead of one per lane: lane l < PFL takes line (l >> 1) of half (l & 1)
+        constexpr int PFL = 2 * (32 * (C / 2) * (int)sizeof(T) / 128 + 1);
+        const bool pf_lane = lane < PFL;
+        const long long pfo = ((lane & 1) ? half : 0) + (long long)(lane >> 1) * (128 / (int)sizeof(T)) - (C / 2) * lane;
+#else
+        constexpr bool pf_lane = true;
+        // prefetches of split rows: even lanes cover the even-column half, odd lanes the other
+        const long long pfo = (SPLIT && (lane & 1)) ? half : 0;
+#endif
 
         T w[WSL][C];
 #pragma unroll
@@ -338,6 +385,24 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
             load_row<C>(w[SHIFT ? k + DEPTH_ROWS + 1 : k], pin + k * pitch);  // rows past either end are zero padding
         }
 #endif
+        // register pipeline of the first touches (colour-split operands: what stage 0 reads, and stage 1's source, was
+        // never read before): loaded one loop trip before use, so their DRAM latency is covered by a trip of work
+        constexpr int FTN = FT ? UNR : 1, FTC = FT ? C / 2 : 1;
+        T ft_sv[FTN][FTC], ft_gn[FTN][FTC], ft_gs[FTN][FTC], ft_ge[FTN][FTC], ft_gw[FTN][FTC], ft_sv1[FTN][FTC];
+        if constexpr (FT) {
+#pragma unroll
+            for (int rr = 0; rr < UNR; ++rr) {
+                const int p = (rr + 1) & 1;
+                const long long same = (long long)rr * pitch + (p ? half : 0), other = (long long)rr * pitch + (p ? 0 : half - 1);
+                if (SRC) ld_operands<FTC, true>(ft_sv[rr], psrc + same);
+                if (SRC) ld_operands<FTC, true>(ft_sv1[rr], psrc + same - pitch);
+                ld_operands<FTC, true>(ft_gn[rr], pgv + same - pitch);
+                ld_operands<FTC, true>(ft_gs[rr], pgv + same);
+                ld_operands<FTC, true>(ft_ge[rr], pgh + same);
+                if (p) ld_operands<FTC, true>(ft_gw[rr], pgh + other);
+                else ld_operands<FTC, false>(ft_gw[rr], pgh + other);
+            }
+        }
         unsigned act = 0, cnt = 0;  // bit s: the row stage s handles this iteration is relaxed / counted
         T mxl[TD];
 #pragma unroll
@@ -368,18 +433,25 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
 #ifndef RBS_TMA
                     prefetch_l2(pin + (long long)L2PF * pitch);
 #endif
-                    if (SRC) prefetch_l2(psrc + (long long)L2PF * pitch);
-                    if (NOISE) {
-                        prefetch_l2(pgh + (long long)L2PF * pitch);
-                        prefetch_l2(pgv + (long long)L2PF * pitch);
+                    if (pf_lane) {
+                        if (SRC) prefetch_l2(psrc + (long long)L2PF * pitch + pfo);
+                        if (NOISE) {
+                            prefetch_l2(pgh + (long long)L2PF * pitch + pfo);
+                            prefetch_l2(pgv + (long long)L2PF * pitch + pfo);
+                        }
                     }
                 }
-                if (SRC) prefetch_l1(psrc + (long long)OPF * pitch);
-                if (NOISE) {
-                    prefetch_l1(pgh + (long long)OPF * pitch);
-                    prefetch_l1(pgv + (long long)OPF * pitch);
+#ifndef RBS_NO_L1PF
+                if (pf_lane) {
+                    if (SRC) prefetch_l1(psrc + (long long)OPF * pitch + pfo);
+                    if (NOISE) {
+                        prefetch_l1(pgh + (long long)OPF * pitch + pfo);
+                        prefetch_l1(pgv + (long long)OPF * pitch + pfo);
+                    }
                 }
-                constexpr int CH = (C + 1) / 2;
+#endif
+                static_assert(C % 2 == 0, "a lane holds whole column pairs");
+                constexpr int CH = C / 2;
                 // operands of the first LA stages are fetched up front, the rest one stage ahead
                 // (all of them when only the source is read; conductances would cost too many registers)
 #ifndef RBS_NOISE_LA
@@ -387,20 +459,67 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
 #endif
                 constexpr int LA = NOISE ? RBS_NOISE_LA : NS;
                 T o_sv[NS][CH], o_gn[NOISE ? NS : 1][CH], o_gs[NOISE ? NS : 1][CH], o_gw[NOISE ? NS : 1][CH], o_ge[NOISE ? NS : 1][CH];
+                // operands of stage s, `ahead` rows further down than this iteration's
+                auto ld_stage = [&](auto s_tag, long long ahead, T *sv, T *gn, T *gs, T *ge, T *gw, bool with_sv, bool with_links,
+                                    bool with_gs) {
+                    constexpr int s = decltype(s_tag)::value;
+                    const long long ro = (ahead - (long long)(LAG * s)) * pitch;
+                    const int p = (rr + 1 + (LAG - 1) * s) & 1;
+                    // colour p of a row: nodes q = p, p+2, ... of the lane sit at [p * half + 0 .. CH) of the split row;
+                    // their west links are the other colour's: same index for p = 1, one to the left for p = 0.
+                    // Unconditional: rows of inactive stages are padding or real rows, both readable.
+                    if constexpr (!SPLIT) {
+                        // natural planes: node q of the lane at [q], its west link at [q - 1]
+#pragma unroll
+                        for (int q = p; q < C; q += 2) {
+                            if (SRC && with_sv) sv[q >> 1] = ld_operand(psrc + ro + q);
+                            if (NOISE && with_links) {
+                                gn[q >> 1] = ld_operand(pgv + ro - pitch + q);
+                                if (with_gs) gs[q >> 1] = ld_operand(pgv + ro + q);
+                                gw[q >> 1] = ld_operand(pgh + ro + q - 1);
+                                ge[q >> 1] = ld_operand(pgh + ro + q);
+                            }
+                        }
+                        return;
+                    }
+                    const long long same = ro + (p ? half : 0), other = ro + (p ? 0 : half - 1);
+                    if (SRC && with_sv) ld_operands<CH, true>(sv, psrc + same);
+                    if (NOISE && with_links) {
+                        ld_operands<CH, true>(gn, pgv + same - pitch);
+                        if (with_gs) ld_operands<CH, true>(gs, pgv + same);
+                        ld_operands<CH, true>(ge, pgh + same);
+                        if (p) ld_operands<CH, true>(gw, pgh + other);
+                        else ld_operands<CH, false>(gw, pgh + other);
+                    }
+                };
                 auto fetch = [&](auto s_tag) {
                     constexpr int s = decltype(s_tag)::value;
-                    const long long ro = -(long long)(LAG * s) * pitch;
-                    const int p = (rr + 1 + (LAG - 1) * s) & 1;
+                    // one row between stages: a stage's south link is the previous stage's north link
+                    constexpr bool own_gs = !(LAG == 1 && s > 0);
+                    if constexpr (FT && s == 0) {
+                        // first touches of the iteration come out of the registers loaded one loop trip ago ...
 #pragma unroll
-                    for (int q = p; q < C; q += 2) {
-                        // unconditional: rows of inactive stages are padding or real rows, both readable
-                        if (SRC) o_sv[s][q >> 1] = ld_operand(psrc + ro + q);
-                        if (NOISE) {
-                            o_gn[s][q >> 1] = ld_operand(pgv + ro - pitch + q);
-                            o_gs[s][q >> 1] = ld_operand(pgv + ro + q);
-                            o_gw[s][q >> 1] = ld_operand(pgh + ro + q - 1);
-                            o_ge[s][q >> 1] = ld_operand(pgh + ro + q);
+                        for (int k = 0; k < CH; ++k) {
+                            if (SRC) o_sv[0][k] = ft_sv[rr][k];
+                            o_gn[0][k] = ft_gn[rr][k];
+                            o_gs[0][k] = ft_gs[rr][k];
+                            o_ge[0][k] = ft_ge[rr][k];
+                            o_gw[0][k] = ft_gw[rr][k];
                         }
+                        // ... and the same loads for the next trip go out now (a whole trip of latency cover)
+                        ld_stage(s_tag, UNR, ft_sv[rr], ft_gn[rr], ft_gs[rr], ft_ge[rr], ft_gw[rr], true, true, true);
+                    } else if constexpr (FT && s == 1) {
+#pragma unroll
+                        for (int k = 0; k < CH; ++k)
+                            if (SRC) o_sv[1][k] = ft_sv1[rr][k];
+                        ld_stage(s_tag, UNR, ft_sv1[rr], nullptr, nullptr, nullptr, nullptr, true, false, false);
+                        ld_stage(s_tag, 0, o_sv[s], o_gn[s], o_gs[s], o_ge[s], o_gw[s], false, true, own_gs);
+                    } else {
+                        ld_stage(s_tag, 0, o_sv[s], o_gn[s], o_gs[s], o_ge[s], o_gw[s], true, true, own_gs);
+                    }
+                    if constexpr (NOISE && !own_gs) {
+#pragma unroll
+                        for (int k = 0; k < CH; ++k) o_gs[s][k] = o_gn[s > 0 ? s - 1 : 0][k];
                     }
                 };
                 static_for<0, LA>(fetch);
@@ -602,9 +721,10 @@ int RBS_FN(apde_plan *p, int64_t n_sweeps, int64_t sweep_base, int phase, cudaSt
         StreamArgs a;
         a.in = p->U<T>(src_buf);
         a.out = p->U<T>(dst_buf);
-        a.src = p->S<T>();
-        a.gh = p->GH<T>();
-        a.gv = p->GV<T>();
+        const bool split = rbs_split((int)sizeof(T), p->d.has_noise);
+        a.src = split ? p->SC<T>() : p->S<T>();
+        a.gh = split ? p->GHC<T>() : p->GH<T>();
+        a.gv = split ? p->GVC<T>() : p->GV<T>();
         a.resid = p->resid.as<T>() + sweep_base + done;
         a.stop = p->stop_flag;
         a.pitch = g.pitch;

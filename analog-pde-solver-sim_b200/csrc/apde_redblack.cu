@@ -394,6 +394,38 @@ int plan_create(apde_plan **out, const apde_plan_desc *d) {
     return APDE_OK;
 }
 
+// Colour-split copy of one operand plane (apde_plan.h): dst[row][pc/2 + (pc&1) * pitch/2] = src[row][pc].
+template <typename T>
+__global__ void __launch_bounds__(256) split_colours_kernel(const T *__restrict__ src, T *__restrict__ dst, long long rows, long long pitch) {
+    const long long half = pitch >> 1, n = rows * half;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        const long long row = k / half, c = k - row * half;
+        const T e = src[row * pitch + 2 * c], o = src[row * pitch + 2 * c + 1];
+        dst[row * pitch + c] = e;
+        dst[row * pitch + half + c] = o;
+    }
+}
+
+int plan_refresh_split(apde_plan *p, cudaStream_t st) {
+    if (!p->split_dirty) return APDE_OK;
+    const size_t bytes = p->plane_elems() * (size_t)p->elem;
+    const long long rows = p->lrows + 2 * p->rowpad;
+    auto one = [&](DevBuf &from, DevBuf &to) -> int {
+        if (!from.p) return APDE_OK;
+        if (!to.p) APDE_TRY(to.alloc(bytes));
+        const int grid = p->sm_count * 8;
+        if (p->elem == 8) split_colours_kernel<double><<<grid, 256, 0, st>>>(from.as<double>(), to.as<double>(), rows, p->pitch);
+        else split_colours_kernel<float><<<grid, 256, 0, st>>>(from.as<float>(), to.as<float>(), rows, p->pitch);
+        return APDE_OK;
+    };
+    APDE_TRY(one(p->src, p->src_cs));
+    APDE_TRY(one(p->gh, p->gh_cs));
+    APDE_TRY(one(p->gv, p->gv_cs));
+    APDE_CUDA(cudaGetLastError());
+    p->split_dirty = false;
+    return APDE_OK;
+}
+
 int plan_ensure_resid(apde_plan *p, int64_t cap) {
     if (cap <= p->resid_cap) return APDE_OK;
     DevBuf nb;
@@ -432,6 +464,7 @@ static int upload_t(apde_plan *p, int64_t win_lo, int64_t win_hi, const double *
     if (p->stage.bytes < nrow * cols * 8) APDE_TRY(p->stage.alloc(nrow * cols * 8));
     double *stage = p->stage.as<double>();
     const int tb = 256, tg = p->sm_count * 8;
+    p->split_dirty = true;
     APDE_CUDA(cudaMemcpyAsync(stage, grid + skip * cols, nrow * cols * 8, cudaMemcpyHostToDevice, 0));
     pack_kernel<T, false><<<tg, tb>>>(stage, r1 - r0, cols, r0, p->U<T>(0), g);
     if (p->d.has_source) {
@@ -491,6 +524,7 @@ template <typename T> static int fill_t(apde_plan *p, const apde_fill_desc *f) {
     APDE_CUDA(cudaDeviceSynchronize());
     p->cur = 0;
     p->filled = true;
+    p->split_dirty = true;
     p->launches += 1;
     return APDE_OK;
 }
@@ -601,8 +635,10 @@ static int run_dispatch(apde_plan *p, int64_t n, int64_t base, int phase, cudaSt
     }
     if (p->variant == 2)
         return sizeof(T) == 8 ? run_pipe_f64(p, n, base, phase, st) : run_pipe_f32(p, n, base, phase, st);
-    if (p->variant == 1)
+    if (p->variant == 1) {
+        APDE_TRY(plan_refresh_split(p, st));
         return sizeof(T) == 8 ? run_stream_f64(p, n, base, phase, st) : run_stream_f32(p, n, base, phase, st);
+    }
     if (phase == 2) return APDE_OK;  // v0 does everything in phase 0/1
     const bool N = p->d.has_noise, S = p->d.has_source;
     if (N && S) return run_v0<T, true, true>(p, n, base, st);
