@@ -112,6 +112,42 @@ __host__ __device__ constexpr bool rbs_split(int elem_bytes, bool noise) {
     return RBS_SPLIT_MODE >= 0 ? RBS_SPLIT_MODE != 0 : (elem_bytes == 8 || noise);
 }
 
+// Asynchronous feed through shared memory (kernels with conductances, one 16-byte vector per lane).  Every iteration
+// the warp copies, with cp.async (16 bytes per lane per instruction, no register and no global-load return path
+// involved), the operand row stage 0 will need RBS_OPS_AHEAD iterations later -- even / odd halves of source, gh and
+// gv, 272 bytes each, contiguous in a ring slot -- plus the next u row of the strip; one commit group per row,
+// cp.async.wait_group + __syncwarp before use.  All stages read their operands with ld.shared at constant offsets
+// from NS + 1 slot addresses, and the u row enters the register window straight from shared memory.
+// Why: with register loads half of all warp cycles sat on the first use after each batch of loads (ncu source view):
+// the first touches of a row come from DRAM and every later load of the warp returns behind them.
+#ifndef RBS_OPS
+#define RBS_OPS 1
+#endif
+#ifndef RBS_OPS_AHEAD
+#define RBS_OPS_AHEAD 4
+#endif
+constexpr int RBS_OPS_SEG = 272;  // bytes per half-row segment: 256 of the strip + 16 of alignment slack / west link
+__host__ __device__ constexpr bool rbs_ops(int elem_bytes, int lane_cols, bool noise) {
+#ifdef RBS_TMA
+    return false;
+#else
+    return RBS_OPS && noise && rbs_split(elem_bytes, noise) && rbs_shift(elem_bytes, noise) && lane_cols * elem_bytes == 16;
+#endif
+}
+__host__ __device__ constexpr int rbs_ops_rows(int td) { return 2 * td + 1 + RBS_OPS_AHEAD; }
+__host__ __device__ constexpr int rbs_ops_row_bytes(bool src) { return (src ? 6 : 4) * RBS_OPS_SEG; }
+__host__ __device__ constexpr int rbs_ops_warp_bytes(int td, bool src) {
+    return (rbs_ops_rows(td) * rbs_ops_row_bytes(src) + (RBS_OPS_AHEAD + 1) * 512 + 127) / 128 * 128;
+}
+__device__ __forceinline__ void cp_async16(unsigned dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 __device__ __forceinline__ void prefetch_l2(const void *p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
@@ -144,7 +180,6 @@ __device__ __forceinline__ void st_vec16(float *p, const float *w) {
                  : "memory");
 }
 
-#ifdef RBS_TMA
 // ---- optional bulk-async (TMA, cp.async.bulk) feed of the u rows: per warp a FIFO ring of row
 // segments in shared memory, filled RBS_TMA_AHEAD rows ahead by one elected lane, completion tracked by
 // one mbarrier per slot.  Keeps many more bytes in flight per SM than the register prefetch can.
@@ -191,7 +226,7 @@ __device__ __forceinline__ void lds_row(T (&w)[C], unsigned addr) {
 #pragma unroll
     for (int k = 0; k < C / PER; ++k) lds_vec16(&w[k * PER], addr + 16 * k);
 }
-#endif
+
 
 // Operand load that stays where it is written: a volatile asm is not sunk towards its first use, so
 // an iteration's operand loads really are in flight before the arithmetic starts.
@@ -232,6 +267,25 @@ __device__ __forceinline__ void ld_operands(T *o, const T *p) {
     }
 }
 
+__device__ __forceinline__ void lds_1(double *o, unsigned a) { asm volatile("ld.shared.f64 %0, [%1];" : "=d"(o[0]) : "r"(a)); }
+__device__ __forceinline__ void lds_1(float *o, unsigned a) { asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o[0]) : "r"(a)); }
+__device__ __forceinline__ void lds_2(double *o, unsigned a) {
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(o[0]), "=d"(o[1]) : "r"(a));
+}
+__device__ __forceinline__ void lds_2(float *o, unsigned a) {
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(o[0]), "=f"(o[1]) : "r"(a));
+}
+template <int N, bool ALIGNED>
+__device__ __forceinline__ void lds_operands(T *o, unsigned a) {
+    if constexpr (ALIGNED && N % 2 == 0) {
+#pragma unroll
+        for (int k = 0; k < N; k += 2) lds_2(&o[k], a + k * (unsigned)sizeof(T));
+    } else {
+#pragma unroll
+        for (int k = 0; k < N; ++k) lds_1(&o[k], a + k * (unsigned)sizeof(T));
+    }
+}
+
 template <int C>
 __device__ __forceinline__ void load_row(T (&w)[C], const T *p) {
     constexpr int PER = 16 / (int)sizeof(T);
@@ -251,7 +305,8 @@ template <int C, int TD, bool NOISE, bool SRC>
 __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C, NOISE)) rb_stream_kernel(const StreamArgs a) {
     constexpr int NS = 2 * TD;             // half-sweep stages
     constexpr int DEPTH_ROWS = 1 + LAG * (NS - 1);            // newest-to-final distance in rows
-    constexpr int NW = ((DEPTH_ROWS + 2 + 1) / 2) * 2 + RBS_PF;  // register window rows (even)
+    constexpr int PF = rbs_ops((int)sizeof(T), C, NOISE) ? 0 : RBS_PF;  // u rows loaded ahead of use (none with the OPS feed)
+    constexpr int NW = ((DEPTH_ROWS + 2 + 1) / 2) * 2 + PF;  // register window rows (even)
     // Two ways to keep the sliding window in registers (SHIFT chosen per variant, rbs_shift()):
     //   rotating: row r+off lives in slot (off + rr) mod NW; nothing ever moves, but the loop body must be unrolled
     //             NW times for the slot numbers to be constants -- 6600 instructions (103 KB) for fp64 depth 3, far
@@ -267,7 +322,13 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
 #define RBS_FT 0
 #endif
     constexpr bool SPLIT = rbs_split((int)sizeof(T), NOISE);
-    constexpr bool FT = RBS_FT && SHIFT && NOISE && SPLIT;
+    constexpr bool OPS = rbs_ops((int)sizeof(T), C, NOISE);
+    constexpr bool FT = RBS_FT && SHIFT && NOISE && SPLIT && !OPS;
+    // OPS rings per warp: OR operand row slots of OROW bytes ([src e|o] gh e|o gv e|o, 272 bytes each), then OU u-row slots
+    constexpr int OA = RBS_OPS_AHEAD, OR = rbs_ops_rows(TD), OROW = rbs_ops_row_bytes(SRC), OSEG = RBS_OPS_SEG;
+    constexpr int OU = OA + 1, OCH = OROW / 16, OCP = (OCH + 31) / 32;  // 16-byte chunks per operand row, copies per lane
+    constexpr int O_GH = SRC ? 2 * OSEG : 0, O_GV = O_GH + 2 * OSEG;
+    static_assert(!OPS || C * sizeof(T) == 16, "OPS: one 16-byte vector per lane");
 #define RBS_SLOT(off) (SHIFT ? ((off) + DEPTH_ROWS + 1 + (rr & 1)) : (((off) + rr + 8 * NW) % NW))
     constexpr int CW = 32 * C;             // columns per warp strip
     constexpr int HCA = ((NS + C - 1) / C) * C;  // column halo, lane aligned
@@ -291,11 +352,17 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
 #pragma unroll
     for (int t = 0; t < TD; ++t) mx[t] = (T)0;
 
+    extern __shared__ __align__(128) unsigned char rbs_smem[];
+    unsigned o_ring = 0, o_uring = 0;  // shared-memory addresses of this warp's operand ring and u-row ring
+    unsigned o_islot = 0, o_wslot = 0, o_iu = 0, o_wu = 0;  // next operand / u slot to fill, and to consume
+    if constexpr (OPS) {
+        o_ring = (unsigned)__cvta_generic_to_shared(rbs_smem) + (unsigned)(threadIdx.x >> 5) * (unsigned)rbs_ops_warp_bytes(TD, SRC);
+        o_uring = o_ring + OR * OROW;
+    }
 #ifdef RBS_TMA
     constexpr int TS = RBS_TMA_SLOTS, TA = RBS_TMA_AHEAD;
     constexpr unsigned ROWB = 32u * C * (unsigned)sizeof(T);  // bytes of one warp row segment
     static_assert(TA + 1 <= TS, "TMA ring too shallow");
-    extern __shared__ __align__(128) unsigned char rbs_smem[];
     const unsigned wsm = (unsigned)__cvta_generic_to_shared(rbs_smem) + (unsigned)(threadIdx.x >> 5) * (TS * ROWB + 8 * TS);
     const unsigned bars = wsm + TS * ROWB;
     if (lane == 0) {
@@ -334,6 +401,48 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
         // operands: row r - 1 (stage 0's row) of the colour-split planes, at the lane's first column pair
         const long long st0 = (long long)(rs - 1) * pitch + (SPLIT ? ((a.padl + jl0) >> 1) : lane_off);
         const T *psrc = a.src + st0, *pgh = a.gh + st0, *pgv = a.gv + st0;
+        // OPS: the strip's half-row segment starts at element o_m0 of a split half row, rounded down to 16 bytes and one
+        // element further left (the west link of the strip's first even node)
+        constexpr int EPV = 16 / (int)sizeof(T);
+        const long long o_m0 = (a.padl + sidx * VW - HCA) >> 1;
+        const long long o_ms = (o_m0 - 1) & ~(long long)(EPV - 1);
+        const unsigned o_lane = (unsigned)((o_m0 - o_ms) + (C / 2) * lane) * (unsigned)sizeof(T);  // this lane's byte offset in a segment
+        // rows fed: stage 0's row of every iteration, rs - 1 .. o_last, in order, each with the u row below it
+        const int o_last = rs + ((r_last - rs) / UNR + 1) * UNR - 2;
+        int o_next = rs - 1;
+        long long o_goff = (long long)(rs - 1) * pitch;  // element offset of the next operand row in a plane
+        const T *o_src[OPS ? OCP : 1];                   // chunk 32k + lane of an operand row: address in row 0
+        if constexpr (OPS) {
+#pragma unroll
+            for (int k = 0; k < OCP; ++k) {
+                const int c = min(32 * k + lane, OCH - 1), seg = c / 17, part = c - seg * 17;
+                const int arr = seg >> 1;
+                const T *plane = SRC ? (arr == 0 ? a.src : arr == 1 ? a.gh : a.gv) : (arr == 0 ? a.gh : a.gv);
+                o_src[k] = plane + ((seg & 1) ? half : 0) + o_ms + part * EPV;
+            }
+        }
+        auto ops_feed = [&]() {
+            if (o_next <= o_last) {
+                const unsigned dst = o_ring + o_islot * OROW + 16u * lane;
+#pragma unroll
+                for (int k = 0; k < OCP; ++k)
+                    if (32 * k + lane < OCH) cp_async16(dst + 512u * k, o_src[k] + o_goff);
+                cp_async16(o_uring + o_iu * 512u + 16u * lane, a.in + o_goff + pitch + lane_off);  // the lane's own vector of u row
+                o_islot = (o_islot + 1 == OR) ? 0 : o_islot + 1;
+                o_iu = (o_iu + 1 == OU) ? 0 : o_iu + 1;
+                o_goff += pitch;
+                ++o_next;
+            }
+            cp_async_commit();  // always: the group count per iteration stays fixed
+        };
+        unsigned oa[OPS ? NS + 1 : 1];  // oa[k]: this lane's address in the ring slot of operand row (stage 0's row) - k
+        if constexpr (OPS) {
+#pragma unroll
+            for (int k = 0; k <= NS; ++k) oa[k] = o_ring + o_lane;
+            __syncwarp();  // every lane is done with the previous item's slots
+#pragma unroll 1
+            for (int k = 0; k < OA; ++k) ops_feed();
+        }
 #ifdef RBS_PF_FEW_LANES
         // one prefetch per 128-byte line instead of one per lane: lane l < PFL takes line (l >> 1) of half (l & 1)
         constexpr int PFL = 2 * (32 * (C / 2) * (int)sizeof(T) / 128 + 1);
@@ -354,7 +463,7 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
         // rows rs .. r_load_end are fed in order: issue TA rows ahead of their consumption
         // exactly the rows the item consumes: RBS_PF in the prologue + one per iteration of the chunked loop
         // (nothing may still be in flight towards this CTA's shared memory when the item -- or the kernel -- ends)
-        const int r_load_end = rs + RBS_PF + ((r_last - rs) / UNR + 1) * UNR - 1;
+        const int r_load_end = rs + PF + ((r_last - rs) / UNR + 1) * UNR - 1;
         const T *pin0 = a.in + (long long)rs * pitch + (a.padl + sidx * VW - HCA);  // lane 0's address of row rs
         int next_issue = rs;
         auto tma_issue_upto = [&](int row_limit) {
@@ -376,12 +485,12 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
             ++consumed;
         };
         __syncwarp();
-        tma_issue_upto(rs + RBS_PF - 1 + TA);
+        tma_issue_upto(rs + PF - 1 + TA);
 #pragma unroll
-        for (int k = 0; k < RBS_PF; ++k) tma_consume(w[k]);
+        for (int k = 0; k < PF; ++k) tma_consume(w[k]);
 #else
 #pragma unroll
-        for (int k = 0; k < RBS_PF; ++k) {
+        for (int k = 0; k < PF; ++k) {
             load_row<C>(w[SHIFT ? k + DEPTH_ROWS + 1 : k], pin + k * pitch);  // rows past either end are zero padding
         }
 #endif
@@ -416,10 +525,22 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
                 // its window slot and nothing waits on it until the row is first used
 #ifdef RBS_TMA
                 __syncwarp();  // every lane is done with the slot that is about to be refilled
-                tma_issue_upto(r + RBS_PF + TA);
-                tma_consume(w[RBS_SLOT(RBS_PF)]);
+                tma_issue_upto(r + PF + TA);
+                tma_consume(w[RBS_SLOT(PF)]);
 #else
-                load_row<C>(w[RBS_SLOT(RBS_PF)], pin + RBS_PF * pitch);
+                if constexpr (OPS) {
+                    cp_async_wait<OA - 1>();  // this lane's part of the oldest group (operand row r - 1, u row r) has landed
+                    __syncwarp();             // ... so has everyone's; and every lane is done with the previous iteration's reads
+                    ops_feed();               // refills the slots last read in the previous iteration
+                    lds_row<C>(w[RBS_SLOT(PF)], o_uring + o_wu * 512u + 16u * lane);
+                    o_wu = (o_wu + 1 == OU) ? 0 : o_wu + 1;
+#pragma unroll
+                    for (int k = NS; k > 0; --k) oa[k] = oa[k - 1];
+                    oa[0] = o_ring + o_wslot * OROW + o_lane;
+                    o_wslot = (o_wslot + 1 == OR) ? 0 : o_wslot + 1;
+                } else {
+                    load_row<C>(w[RBS_SLOT(PF)], pin + PF * pitch);
+                }
 #endif
                 act = (act << 1) | (((unsigned)(r - 2 - ra) < upd_span) ? 1u : 0u);
                 cnt = (cnt << 1) | (((unsigned)(r - 1 - rb0) < own_span) ? 1u : 0u);
@@ -433,7 +554,7 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
 #ifndef RBS_TMA
                     prefetch_l2(pin + (long long)L2PF * pitch);
 #endif
-                    if (pf_lane) {
+                    if (pf_lane && !OPS) {
                         if (SRC) prefetch_l2(psrc + (long long)L2PF * pitch + pfo);
                         if (NOISE) {
                             prefetch_l2(pgh + (long long)L2PF * pitch + pfo);
@@ -442,7 +563,7 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
                     }
                 }
 #ifndef RBS_NO_L1PF
-                if (pf_lane) {
+                if (pf_lane && !OPS) {
                     if (SRC) prefetch_l1(psrc + (long long)OPF * pitch + pfo);
                     if (NOISE) {
                         prefetch_l1(pgh + (long long)OPF * pitch + pfo);
@@ -468,6 +589,19 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
                     // colour p of a row: nodes q = p, p+2, ... of the lane sit at [p * half + 0 .. CH) of the split row;
                     // their west links are the other colour's: same index for p = 1, one to the left for p = 0.
                     // Unconditional: rows of inactive stages are padding or real rows, both readable.
+                    if constexpr (OPS) {
+                        // shared-memory ring: row slots oa[s] (this stage's row) and oa[s + 1] (the row above)
+                        const unsigned b = oa[s], bn = oa[s + 1];
+                        if (SRC && with_sv) lds_operands<CH, true>(sv, b + (p ? OSEG : 0));
+                        if (with_links) {
+                            lds_operands<CH, true>(gn, bn + O_GV + (p ? OSEG : 0));
+                            if (with_gs) lds_operands<CH, true>(gs, b + O_GV + (p ? OSEG : 0));
+                            lds_operands<CH, true>(ge, b + O_GH + (p ? OSEG : 0));
+                            if (p) lds_operands<CH, true>(gw, b + O_GH);
+                            else lds_operands<CH, false>(gw, b + O_GH + OSEG - (unsigned)sizeof(T));
+                        }
+                        return;
+                    }
                     if constexpr (!SPLIT) {
                         // natural planes: node q of the lane at [q], its west link at [q - 1]
 #pragma unroll
@@ -635,7 +769,7 @@ int launch_pass(apde_plan *p, StreamArgs &a, const BlockReq &rq, cudaStream_t st
 #ifdef RBS_TMA
     constexpr size_t smem = (size_t)(RBS_THREADS / 32) * (RBS_TMA_SLOTS * 32 * C * sizeof(T) + 8 * RBS_TMA_SLOTS);
 #else
-    constexpr size_t smem = 0;
+    constexpr size_t smem = rbs_ops((int)sizeof(T), C, NOISE) ? (size_t)(RBS_THREADS / 32) * rbs_ops_warp_bytes(TD, SRC) : 0;
 #endif
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
