@@ -99,8 +99,21 @@ constexpr int rbs_min_blocks(int elem_bytes, int lane_cols, bool noise) {
 #ifndef RBS_SHIFT_MODE
 #define RBS_SHIFT_MODE -1  // -1: per variant (default), 0: always rotating, 1: always shifted
 #endif
-__host__ __device__ constexpr bool rbs_shift(int elem_bytes, bool noise) {
-    return RBS_SHIFT_MODE >= 0 ? RBS_SHIFT_MODE != 0 : (elem_bytes == 8 || noise);
+#ifndef RBS_OPS
+#define RBS_OPS 2  // 0: no asynchronous shared-memory feed, 1: kernels with conductances, 2: every kernel
+#endif
+// asynchronous shared-memory feed (described below): needs one 16-byte vector per lane
+__host__ __device__ constexpr bool rbs_ops(int elem_bytes, int lane_cols, bool noise) {
+#ifdef RBS_TMA
+    return false;
+#else
+    // one 16-byte vector per lane, or two without conductances (their six segments per row would not fit)
+    return (RBS_OPS == 2 || (RBS_OPS == 1 && noise)) && (lane_cols * elem_bytes == 16 || (lane_cols * elem_bytes == 32 && !noise)) &&
+           RBS_SHIFT_MODE != 0;
+#endif
+}
+__host__ __device__ constexpr bool rbs_shift(int elem_bytes, int lane_cols, bool noise) {
+    return RBS_SHIFT_MODE >= 0 ? RBS_SHIFT_MODE != 0 : (elem_bytes == 8 || noise || rbs_ops(elem_bytes, lane_cols, noise));
 }
 
 // Operand planes read by the kernel: colour-split copies (apde_plan.h) or the natural ones.  Split wins wherever it was
@@ -108,8 +121,8 @@ __host__ __device__ constexpr bool rbs_shift(int elem_bytes, bool noise) {
 #ifndef RBS_SPLIT_MODE
 #define RBS_SPLIT_MODE -1  // -1: per variant (default), 0: natural everywhere, 1: split everywhere
 #endif
-__host__ __device__ constexpr bool rbs_split(int elem_bytes, bool noise) {
-    return RBS_SPLIT_MODE >= 0 ? RBS_SPLIT_MODE != 0 : (elem_bytes == 8 || noise);
+__host__ __device__ constexpr bool rbs_split(int elem_bytes, int lane_cols, bool noise) {
+    return rbs_ops(elem_bytes, lane_cols, noise) || (RBS_SPLIT_MODE >= 0 ? RBS_SPLIT_MODE != 0 : (elem_bytes == 8 || noise));
 }
 
 // Asynchronous feed through shared memory (kernels with conductances, one 16-byte vector per lane).  Every iteration
@@ -120,24 +133,15 @@ __host__ __device__ constexpr bool rbs_split(int elem_bytes, bool noise) {
 // from NS + 1 slot addresses, and the u row enters the register window straight from shared memory.
 // Why: with register loads half of all warp cycles sat on the first use after each batch of loads (ncu source view):
 // the first touches of a row come from DRAM and every later load of the warp returns behind them.
-#ifndef RBS_OPS
-#define RBS_OPS 1
-#endif
 #ifndef RBS_OPS_AHEAD
 #define RBS_OPS_AHEAD 4
 #endif
-constexpr int RBS_OPS_SEG = 272;  // bytes per half-row segment: 256 of the strip + 16 of alignment slack / west link
-__host__ __device__ constexpr bool rbs_ops(int elem_bytes, int lane_cols, bool noise) {
-#ifdef RBS_TMA
-    return false;
-#else
-    return RBS_OPS && noise && rbs_split(elem_bytes, noise) && rbs_shift(elem_bytes, noise) && lane_cols * elem_bytes == 16;
-#endif
-}
+// bytes per half-row segment: the strip's 32 * C / 2 elements + 16 of alignment slack / west link (vb = bytes per lane per u row)
+__host__ __device__ constexpr int rbs_ops_seg(int vb) { return 16 * vb + 16; }
 __host__ __device__ constexpr int rbs_ops_rows(int td) { return 2 * td + 1 + RBS_OPS_AHEAD; }
-__host__ __device__ constexpr int rbs_ops_row_bytes(bool src) { return (src ? 6 : 4) * RBS_OPS_SEG; }
-__host__ __device__ constexpr int rbs_ops_warp_bytes(int td, bool src) {
-    return (rbs_ops_rows(td) * rbs_ops_row_bytes(src) + (RBS_OPS_AHEAD + 1) * 512 + 127) / 128 * 128;
+__host__ __device__ constexpr int rbs_ops_row_bytes(int vb, bool src, bool noise) { return ((src ? 2 : 0) + (noise ? 4 : 0)) * rbs_ops_seg(vb); }
+__host__ __device__ constexpr int rbs_ops_warp_bytes(int vb, int td, bool src, bool noise) {
+    return (rbs_ops_rows(td) * rbs_ops_row_bytes(vb, src, noise) + (RBS_OPS_AHEAD + 1) * 32 * vb + 127) / 128 * 128;
 }
 __device__ __forceinline__ void cp_async16(unsigned dst, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -314,21 +318,24 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
     //   shifted : row r+off lives in slot off + DEPTH_ROWS + 1 + (rr & 1) and the whole window moves down two slots
     //             every second iteration: unrolled 2x (1744 instructions), (NW-1)*C register moves per two iterations,
     //             and ~35 fewer live registers -- depth 4 then fits without spills (fp64 Poisson 230 registers).
-    constexpr bool SHIFT = rbs_shift((int)sizeof(T), NOISE);
+    constexpr bool SHIFT = rbs_shift((int)sizeof(T), C, NOISE);
     constexpr int WSL = SHIFT ? NW + 1 : NW;  // slots
     constexpr int UNR = SHIFT ? 2 : NW;       // unroll period
     static_assert(!SHIFT || LAG == 1, "the shifted window assumes one row between stages");
 #ifndef RBS_FT
 #define RBS_FT 0
 #endif
-    constexpr bool SPLIT = rbs_split((int)sizeof(T), NOISE);
+    constexpr bool SPLIT = rbs_split((int)sizeof(T), C, NOISE);
     constexpr bool OPS = rbs_ops((int)sizeof(T), C, NOISE);
     constexpr bool FT = RBS_FT && SHIFT && NOISE && SPLIT && !OPS;
     // OPS rings per warp: OR operand row slots of OROW bytes ([src e|o] gh e|o gv e|o, 272 bytes each), then OU u-row slots
-    constexpr int OA = RBS_OPS_AHEAD, OR = rbs_ops_rows(TD), OROW = rbs_ops_row_bytes(SRC), OSEG = RBS_OPS_SEG;
+    constexpr int VB = C * (int)sizeof(T);  // bytes per lane per u row
+    constexpr int OA = RBS_OPS_AHEAD, OR = rbs_ops_rows(TD), OROW = rbs_ops_row_bytes(VB, SRC, NOISE), OSEG = rbs_ops_seg(VB);
+    constexpr int OUB = 32 * VB, OSC = OSEG / 16;  // bytes per u-row slot, 16-byte chunks per segment
     constexpr int OU = OA + 1, OCH = OROW / 16, OCP = (OCH + 31) / 32;  // 16-byte chunks per operand row, copies per lane
     constexpr int O_GH = SRC ? 2 * OSEG : 0, O_GV = O_GH + 2 * OSEG;
-    static_assert(!OPS || C * sizeof(T) == 16, "OPS: one 16-byte vector per lane");
+    constexpr int OCPA = OCP > 0 ? OCP : 1;
+    static_assert(!OPS || VB == 16 || VB == 32, "OPS: one or two 16-byte vectors per lane");
 #define RBS_SLOT(off) (SHIFT ? ((off) + DEPTH_ROWS + 1 + (rr & 1)) : (((off) + rr + 8 * NW) % NW))
     constexpr int CW = 32 * C;             // columns per warp strip
     constexpr int HCA = ((NS + C - 1) / C) * C;  // column halo, lane aligned
@@ -356,7 +363,7 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
     unsigned o_ring = 0, o_uring = 0;  // shared-memory addresses of this warp's operand ring and u-row ring
     unsigned o_islot = 0, o_wslot = 0, o_iu = 0, o_wu = 0;  // next operand / u slot to fill, and to consume
     if constexpr (OPS) {
-        o_ring = (unsigned)__cvta_generic_to_shared(rbs_smem) + (unsigned)(threadIdx.x >> 5) * (unsigned)rbs_ops_warp_bytes(TD, SRC);
+        o_ring = (unsigned)__cvta_generic_to_shared(rbs_smem) + (unsigned)(threadIdx.x >> 5) * (unsigned)rbs_ops_warp_bytes(C * (int)sizeof(T), TD, SRC, NOISE);
         o_uring = o_ring + OR * OROW;
     }
 #ifdef RBS_TMA
@@ -411,13 +418,13 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
         const int o_last = rs + ((r_last - rs) / UNR + 1) * UNR - 2;
         int o_next = rs - 1;
         long long o_goff = (long long)(rs - 1) * pitch;  // element offset of the next operand row in a plane
-        const T *o_src[OPS ? OCP : 1];                   // chunk 32k + lane of an operand row: address in row 0
+        const T *o_src[OPS ? OCPA : 1];                  // chunk 32k + lane of an operand row: address in row 0
         if constexpr (OPS) {
 #pragma unroll
             for (int k = 0; k < OCP; ++k) {
-                const int c = min(32 * k + lane, OCH - 1), seg = c / 17, part = c - seg * 17;
+                const int c = min(32 * k + lane, OCH - 1), seg = c / OSC, part = c - seg * OSC;
                 const int arr = seg >> 1;
-                const T *plane = SRC ? (arr == 0 ? a.src : arr == 1 ? a.gh : a.gv) : (arr == 0 ? a.gh : a.gv);
+                const T *plane = SRC ? (arr == 0 ? a.src : arr == 1 ? a.gh : a.gv) : (arr == 0 ? a.gh : a.gv);  // (no NOISE: src only)
                 o_src[k] = plane + ((seg & 1) ? half : 0) + o_ms + part * EPV;
             }
         }
@@ -427,7 +434,9 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
 #pragma unroll
                 for (int k = 0; k < OCP; ++k)
                     if (32 * k + lane < OCH) cp_async16(dst + 512u * k, o_src[k] + o_goff);
-                cp_async16(o_uring + o_iu * 512u + 16u * lane, a.in + o_goff + pitch + lane_off);  // the lane's own vector of u row
+#pragma unroll
+                for (int k = 0; k < VB / 16; ++k)  // the lane's own vectors of the u row
+                    cp_async16(o_uring + o_iu * (unsigned)OUB + (unsigned)VB * lane + 16u * k, a.in + o_goff + pitch + lane_off + k * EPV);
                 o_islot = (o_islot + 1 == OR) ? 0 : o_islot + 1;
                 o_iu = (o_iu + 1 == OU) ? 0 : o_iu + 1;
                 o_goff += pitch;
@@ -532,7 +541,7 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
                     cp_async_wait<OA - 1>();  // this lane's part of the oldest group (operand row r - 1, u row r) has landed
                     __syncwarp();             // ... so has everyone's; and every lane is done with the previous iteration's reads
                     ops_feed();               // refills the slots last read in the previous iteration
-                    lds_row<C>(w[RBS_SLOT(PF)], o_uring + o_wu * 512u + 16u * lane);
+                    lds_row<C>(w[RBS_SLOT(PF)], o_uring + o_wu * (unsigned)OUB + (unsigned)VB * lane);
                     o_wu = (o_wu + 1 == OU) ? 0 : o_wu + 1;
 #pragma unroll
                     for (int k = NS; k > 0; --k) oa[k] = oa[k - 1];
@@ -593,7 +602,7 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
                         // shared-memory ring: row slots oa[s] (this stage's row) and oa[s + 1] (the row above)
                         const unsigned b = oa[s], bn = oa[s + 1];
                         if (SRC && with_sv) lds_operands<CH, true>(sv, b + (p ? OSEG : 0));
-                        if (with_links) {
+                        if (NOISE && with_links) {
                             lds_operands<CH, true>(gn, bn + O_GV + (p ? OSEG : 0));
                             if (with_gs) lds_operands<CH, true>(gs, b + O_GV + (p ? OSEG : 0));
                             lds_operands<CH, true>(ge, b + O_GH + (p ? OSEG : 0));
@@ -769,7 +778,7 @@ int launch_pass(apde_plan *p, StreamArgs &a, const BlockReq &rq, cudaStream_t st
 #ifdef RBS_TMA
     constexpr size_t smem = (size_t)(RBS_THREADS / 32) * (RBS_TMA_SLOTS * 32 * C * sizeof(T) + 8 * RBS_TMA_SLOTS);
 #else
-    constexpr size_t smem = rbs_ops((int)sizeof(T), C, NOISE) ? (size_t)(RBS_THREADS / 32) * rbs_ops_warp_bytes(TD, SRC) : 0;
+    constexpr size_t smem = rbs_ops((int)sizeof(T), C, NOISE) ? (size_t)(RBS_THREADS / 32) * rbs_ops_warp_bytes(C * (int)sizeof(T), TD, SRC, NOISE) : 0;
 #endif
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
@@ -855,7 +864,8 @@ int RBS_FN(apde_plan *p, int64_t n_sweeps, int64_t sweep_base, int phase, cudaSt
         StreamArgs a;
         a.in = p->U<T>(src_buf);
         a.out = p->U<T>(dst_buf);
-        const bool split = rbs_split((int)sizeof(T), p->d.has_noise);
+        const int lane_cols = p->lane_vectors == 2 ? RBS_C2 : RBS_C1;
+        const bool split = rbs_split((int)sizeof(T), lane_cols, p->d.has_noise);
         a.src = split ? p->SC<T>() : p->S<T>();
         a.gh = split ? p->GHC<T>() : p->GH<T>();
         a.gv = split ? p->GVC<T>() : p->GV<T>();
@@ -869,7 +879,6 @@ int RBS_FN(apde_plan *p, int64_t n_sweeps, int64_t sweep_base, int phase, cudaSt
         a.row0 = g.row0;
         a.own_lo = g.own_lo;
         a.own_hi = g.own_hi;
-        const int lane_cols = p->lane_vectors == 2 ? RBS_C2 : RBS_C1;
         const int HCA = ((2 * td + lane_cols - 1) / lane_cols) * lane_cols;
         const int VW = 32 * lane_cols - 2 * HCA;
         a.n_strips = (g.cols + VW - 1) / VW;

@@ -308,9 +308,10 @@ __global__ void stop_check_kernel(const T *__restrict__ resid, int n, double tol
 // Tuning / cross-check knobs from the environment (read at plan creation and whenever a cached plan is reused).
 static void apply_env_knobs(apde_plan *p) {
     p->variant = default_rb_variant();
-    // 16-byte vectors per lane per row: 4 columns per lane for fp32 and fp64; fp64 with mismatch runs 2 columns per lane
-    // (half the window and operand registers: depth 3 at 228 registers, 253 vs 214 GLUP/s -- profiles/r2_rb_sweep_shift.txt)
-    p->lane_vectors = (p->d.dtype_bytes == 8 && !p->d.has_noise) ? 2 : 1;
+    // 16-byte vectors per lane per row, measured per variant at 16384^2 (profiles/r2_rb_sweep_async.txt): with conductances
+    // one (the six operand segments per row of two would not fit the shared-memory rings); without, two for fp64
+    // (Poisson 660 vs 554 GLUP/s) and for fp32 Laplace (1894 vs 1556), one for fp32 Poisson (1284 vs 1187)
+    p->lane_vectors = p->d.has_noise ? 1 : (p->d.dtype_bytes == 8 || !p->d.has_source) ? 2 : 1;
     if (const char *v = getenv("APDE_LANE_VECTORS")) p->lane_vectors = atoi(v) == 2 ? 2 : 1;
     p->row_block = 256;
     p->row_block_forced = false;
@@ -802,10 +803,11 @@ int max_temporal_depth() {
 // Fused depth the one-shot solves use when the caller passes temporal_depth <= 0: the measured best per
 // variant on B200 (profiles/).
 int default_temporal_depth(int elem, bool noise) {
-    // 16384^2 on B200 (profiles/r2_rb_sweep_shift.txt): depth 4 with the shifted register window (fp64 Poisson, fp32
-    // with mismatch); fp64 with mismatch depth 3 at 2 columns per lane; fp32 Poisson the rotating window at depth 3
-    if (elem == 8) return noise ? 3 : 4;
-    return noise ? 4 : 3;
+    // 16384^2 on B200 (profiles/r2_rb_sweep_async.txt): with the asynchronous shared-memory feed every variant is
+    // fastest at the deepest instantiated depth
+    (void)elem;
+    (void)noise;
+    return 4;
 }
 
 static apde_plan *g_cached_plan = nullptr;  // never destroyed at exit (the context may be gone by then)

@@ -69,7 +69,7 @@ int apde_solve_exact_f64_path(double *grid, const double *noise_h, const double 
  * sweeps.  Convergence is tested every `check_every` sweeps: iterations_run is a multiple of
  * check_every (or max_iter) and residual_history holds every executed sweep.
  *   _f64: fp64 arithmetic;  _f32: fp32 arithmetic (host arrays stay float64, converted on device).
- * check_every <= 0 => 32; temporal_depth <= 0 => library default (fp64: 4, 3 with mismatch; fp32: 3, 4 with mismatch); values above the
+ * check_every <= 0 => 32; temporal_depth <= 0 => library default (4); values above the
  * kernel family's maximum (4; 6 for APDE_RB_VARIANT=v2) are clamped.
  * ---------------------------------------------------------------------------------------- */
 int apde_solve_redblack_f64(double *grid, const double *noise_h, const double *noise_v,
