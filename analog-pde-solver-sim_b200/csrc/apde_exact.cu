@@ -570,6 +570,216 @@ __global__ void __launch_bounds__(1024, 1) exact_ring2_kernel(K2Params p, int kb
 }
 
 // ------------------------------------------------------------------------------------------
+// K2c: row bands, every thread walks along ONE grid row (round 2; the default for large grids).
+//
+// The interior rows are cut into bands of NT rows; a CTA owns (sweep slot, band) and thread r of it
+// owns row i = 1 + band*NT + r for the whole launch.  At CTA step S thread r handles column
+// j = (S - r) mod cols - 1 of task (S - r) div cols (task n of slot s = sweep s + n*Gs), i.e. all
+// threads of a CTA sit on one anti-diagonal (unit-stride accesses in the diagonal-major layout) and a
+// thread that finishes its row starts the same row of the CTA's next sweep in the next step -- no
+// pipeline drain between the sweeps of a CTA.  Columns -1 and 0 are two bookkeeping steps per row
+// that pull the west boundary value and the west link through the same register path as every
+// other column (so no step ever waits for a special-case load).
+// What a node needs and where it comes from:
+//   west  u_t(i,j-1)      the thread's own previous result              register
+//   west link nh[i,j-1]   the thread's own previous east link            register
+//   old   u_{t-1}(i,j)    the thread's own previous east operand         register
+//   north u_t(i-1,j)      thread r-1's previous result                   shuffle (lane 0: shared memory;
+//                                                                        thread 0: the band above, L2)
+//   south u_{t-1}(i+1,j)  thread r+1's east operand of this step         shuffle (lane 31 / last row: L2)
+//   east  u_{t-1}(i,j+1)  written by the CTA of sweep t-1                ONE 8-byte L2 load, requested a step ahead
+//   links nv[i-1,j], nv[i,j], nh[i,j], source                            __ldg (north link: an L1 hit, it was
+//                                                                        the neighbour's south link a step ago)
+// => 8 B of u + 32 B of links loaded and 8 B stored per update through L2, against 40 + 64 + 8 B for K2
+// (which re-reads all five u operands and all four links per node).
+// Ordering between CTAs: every CTA publishes the number of steps it has completed (release, every kb
+// steps); before a batch of kb steps three lanes acquire-poll
+//   A  (slot-1, band)    >= S+3      east/south operands (+1: they are requested one step ahead)
+//   B  (slot-1, band+1)  >= S-NT+3   south operand of the band's last row
+//   C  (slot,   band-1)  >= S+NT+1   north operand of the band's first row (also the WAR on that row)
+// with S the last step of the batch; the predecessor of slot 0 is slot Gs-1 one task earlier (-cols).
+// A thread runs its next task while later rows still finish the current one, so the ring of sweep
+// slots must be short enough for the slot-0 CTA never to wait for itself: the host keeps
+// Gs * (3*kb + 4) <= cols (tools/band_protocol_sim.py replays the protocol on the CPU).  One __syncthreads per step
+// (north hand-off between warps), one more where progress is published.
+// ------------------------------------------------------------------------------------------
+// Branch-free form of exact_div for the band kernel: the quotient of the screened fast path, or the correctly signed
+// zero, selected by predicates; anything else (unscreened link, tiny / huge / non-finite numerator) raises `slow` and
+// the caller redoes the node with the general division.  No branch per division, so the four divisions of a node
+// interleave in the fp64 pipe instead of running one behind the other.
+__device__ __forceinline__ double band_div(double a, double2 link, bool &slow) {
+    const double b = link.x, y = link.y;
+    const unsigned hi = (unsigned)__double2hiint(a);
+    const bool inr = ((hi & 0x7ff00000u) - (323u << 20)) <= (1400u << 20);  // |a| in [2^-700, 2^700]
+    double q = __dmul_rn(a, y);
+    double r = __fma_rn(-q, b, a);
+    q = __fma_rn(r, y, q);
+    r = __fma_rn(-q, b, a);
+    q = __fma_rn(r, y, q);
+    const double z = __hiloint2double((int)((hi ^ (unsigned)__double2hiint(b)) & 0x80000000u), 0);
+    slow = slow || (y == 0.0) || !(inr || a == 0.0);
+    return inr ? q : z;
+}
+
+// the node with four general IEEE divisions (what exact_div falls back to; same bits by construction), out of line so
+// that the rare path costs the hot loop no registers
+template <bool HAS_SRC>
+__device__ __noinline__ double relax_node_general(double un, double us, double uw, double ue, double bn, double bs, double bw,
+                                                  double be, double src) {
+    double acc = __dadd_rn(__ddiv_rn(un, bn), __ddiv_rn(us, bs));
+    acc = __dadd_rn(acc, __ddiv_rn(uw, bw));
+    acc = __dadd_rn(acc, __ddiv_rn(ue, be));
+    if (HAS_SRC) acc = __dsub_rn(acc, src);
+    return __dmul_rn(acc, 0.25);
+}
+
+template <bool HAS_NOISE, bool HAS_SRC, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) exact_band_kernel(K2Params p, int B, int Gs, int kb) {
+    const int rows = p.rows, cols = p.cols;
+    const unsigned P = (unsigned)p.P;  // element offsets fit 32 bits (checked by the host): one IMAD.WIDE per address
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int slot = blockIdx.x / B, band = blockIdx.x - slot * B;
+    const int CP = cols;  // steps per task: columns -1 .. cols-2
+    const int ntasks = (int)((p.n_sweeps - slot + Gs - 1) / Gs);  // the launch guarantees slot < n_sweeps
+    const int pslot = slot == 0 ? Gs - 1 : slot - 1;
+    const int ntasks_p = (int)((p.n_sweeps - pslot + Gs - 1) / Gs);
+    const int i0 = 1 + band * NT;
+    const int rows_b = min(NT, rows - 1 - i0);  // rows of this band (>= 1)
+    const int i = i0 + tid;
+    const bool row_ok = tid < rows_b;
+    const bool sx = row_ok && (lane == 31 || tid == rows_b - 1);  // south operand comes from memory
+    const long long Stot = (long long)ntasks * CP + NT - 1, totP = (long long)ntasks_p * CP + NT - 1;
+    __shared__ double nbuf[2][NT / 32];
+    double *__restrict__ U = p.U;
+    const double2 *__restrict__ LH = p.LH, *__restrict__ LV = p.LV;
+    const double *__restrict__ SRC = p.S;
+
+    // what this thread polls before a batch of kb steps (threads 0..2), as  flag >= min(S + kb + f_add, f_cap)
+    const unsigned long long *f_ptr = nullptr;
+    long long f_add = 0, f_cap = 0;
+    {
+        const long long adj = slot == 0 ? CP : 0;
+        if (tid == 0 && Gs > 1) {
+            f_ptr = p.progress + ((size_t)pslot * B + band) * 16;
+            f_add = 2 - adj;
+            f_cap = totP;
+        }
+        if (tid == 1 && band + 1 < B) {
+            f_ptr = p.progress + ((size_t)pslot * B + band + 1) * 16;
+            f_add = 2 - NT - adj;
+            f_cap = totP;
+        }
+        if (tid == 2 && band > 0) {
+            f_ptr = p.progress + ((size_t)slot * B + band - 1) * 16;
+            f_add = NT;
+            f_cap = Stot;
+        }
+    }
+    unsigned long long *fme = p.progress + (size_t)blockIdx.x * 16;
+
+    const unsigned off0 = (unsigned)(i - 1) * P + (unsigned)i;  // node (i, -1)
+    unsigned off = off0;
+    int n = 0;
+    int jx = -tid;  // column jx - 1; negative: the row has not started yet
+    double uw = 0.0, old = 0.0, mx = 0.0, ue_c = 0.0, us_c = 0.0, un_c = 0.0;
+    double2 lw = make_double2(1.0, 1.0);
+    if (tid == 0 && ntasks > 0) ue_c = __ldcg(U + off0 + P);  // u(i,0), a ring value
+
+    int kbc = 0;
+    unsigned par = 0;  // S & 1
+    for (long long S = 0; S < Stot; ++S) {
+        if (kbc == 0) {
+            // publish BEFORE polling: a CTA that is waiting for its predecessors must not withhold the steps it has
+            // already completed from its successors (withholding adds kb steps of lag per hop around the ring of
+            // slots -- measured as a deadlock at 15 slots x kb 8 on 300 columns)
+            if (S > 0) {
+                __syncthreads();  // every thread's stores of step S-1 are ordered before the release
+                if (tid == NT - 1) st_release_u64(fme, (unsigned long long)S);
+            }
+            if (f_ptr != nullptr) {
+                const long long need = min(S + kb + f_add, f_cap);
+                if (need > 0)
+                    while (ld_acquire_u64(f_ptr) < (unsigned long long)need) {
+                    }
+            }
+        }
+        __syncthreads();
+        if (++kbc == kb) kbc = 0;
+
+        // ---- the thread's next step, and the u operands it will need (one step of cover for the L2 round trip)
+        int jxn = jx + 1, nn = n;
+        unsigned offn = jx >= 0 ? off + P : off0;
+        if (jxn == CP) {
+            jxn = 0;
+            offn = off0;
+            nn = n + 1;
+        }
+        const bool actn = row_ok && jxn >= 0 && nn < ntasks;
+        double ue_n = 0.0, us_n = 0.0, un_n = 0.0;
+        if (actn) {
+            ue_n = __ldcg(U + (offn + P));
+            if (jxn >= 2) {
+                if (sx) us_n = __ldcg(U + (offn + P + 1u));
+                if (tid == 0) un_n = __ldcg(U + (offn - P - 1u));
+                if (HAS_NOISE) {
+                    prefetch_l1_line(LV + offn);
+                    prefetch_l1_line(LH + offn);
+                }
+                if (HAS_SRC) prefetch_l1_line(SRC + offn);
+            }
+        }
+        // ---- this step
+        const bool act = row_ok && jx >= 0 && n < ntasks;
+        double us = __shfl_down_sync(0xffffffffu, ue_c, 1);
+        double un = __shfl_up_sync(0xffffffffu, uw, 1);
+        if (sx) us = us_c;
+        if (lane == 0) un = (tid == 0) ? un_c : nbuf[par ^ 1u][warp > 0 ? warp - 1 : 0];  // written in step S-1
+        double val = old;  // the boundary column passes through
+        double2 le = make_double2(1.0, 1.0);
+        if (act && jx >= 1) {
+            if (HAS_NOISE) le = __ldg(LH + off);
+            if (jx >= 2) {
+                double sv = 0.0;
+                if (HAS_SRC) sv = __ldg(SRC + off);
+                if (HAS_NOISE) {
+                    const double2 ln = __ldg(LV + (off - P - 1u)), ls = __ldg(LV + off);
+                    bool slow = false;
+                    const double qn = band_div(un, ln, slow), qs = band_div(us, ls, slow);
+                    const double qw = band_div(uw, lw, slow), qe = band_div(ue_c, le, slow);
+                    double acc = __dadd_rn(__dadd_rn(__dadd_rn(qn, qs), qw), qe);  // solver.py:275, left-associative
+                    if (HAS_SRC) acc = __dsub_rn(acc, sv);
+                    val = __dmul_rn(acc, 0.25);
+                    if (slow) val = relax_node_general<HAS_SRC>(un, us, uw, ue_c, ln.x, ls.x, lw.x, le.x, sv);
+                } else {
+                    val = relax_node<false, HAS_SRC>(un, us, uw, ue_c, le, le, le, le, sv);
+                }
+                mx = max_ignore_nan(mx, fabs(__dsub_rn(val, old)));
+                __stcg(U + off, val);
+                if (jx == CP - 1) {  // end of the row: this sweep's residual (solver.py:277-281)
+                    atomic_max_nonneg(p.hist + (slot + (long long)n * Gs), mx);
+                    mx = 0.0;
+                }
+            }
+        }
+        if (act) {
+            uw = val;
+            old = ue_c;
+            lw = le;
+        }
+        if (lane == 31) nbuf[par][warp] = uw;
+        par ^= 1u;
+        jx = jxn;
+        off = offn;
+        n = nn;
+        ue_c = ue_n;
+        us_c = us_n;
+        un_c = un_n;
+    }
+    __syncthreads();
+    if (tid == NT - 1) st_release_u64(fme, (unsigned long long)Stot);
+}
+
+// ------------------------------------------------------------------------------------------
 // host drivers
 // ------------------------------------------------------------------------------------------
 template <typename K>
@@ -667,9 +877,12 @@ static int solve_small(double *grid, const double *nh, const double *nv, const d
 struct RingCfg {
     int block = 1024;
     int npt = 0;       // 0 => K2 (generic kernel), else K2b with this many nodes per thread
-    int kb = 8;        // diagonals per progress exchange (K2b)
+    int kb = 8;        // diagonals per progress exchange (K2b) / steps per progress exchange (K2c)
     size_t smem = 0;
     int grid_max = 0;  // co-resident CTAs
+    int band_nt = 0;   // > 0: K2c (row bands) with this many rows per band
+    int bands = 1;     // K2c: CTAs per sweep
+    int slots_max = 0; // sweeps in flight at most (K2/K2b: grid_max)
 };
 
 template <bool N, bool S>
@@ -679,6 +892,9 @@ static const void *ring_fn(int npt) {
     // beat the 128-register shapes with four nodes in flight (256 x 2: 71; 512 x 1: 62 / 43) -- more warps hide the
     // L2 latency better than more loads per warp; without links four nodes in flight fit 64 registers: 165 -> 205.
     switch (npt) {
+        case 1064: return (const void *)exact_band_kernel<N, S, 64, 8>;  // K2c: 1000 + rows per band
+        case 1256: return (const void *)exact_band_kernel<N, S, 256, 4>;
+        case 1512: return (const void *)exact_band_kernel<N, S, 512, 2>;
         case -1024: return (const void *)exact_ring_kernel<N, S, 1024, 1, N ? 1 : 4>;
         case -512: return (const void *)exact_ring_kernel<N, S, 512, 2, N ? 1 : 4>;
         case -256: return (const void *)exact_ring_kernel<N, S, 256, 2, 4>;
@@ -695,12 +911,18 @@ static const void *ring_fn(bool noise, bool src, int npt) {
     return ring_fn<false, false>(npt);
 }
 
-static int ring_dispatch(bool noise, bool src, const K2Params &p, const RingCfg &cfg, int grid, cudaStream_t st) {
+// `slots` = sweeps in flight (CTAs for K2/K2b; K2c launches slots * bands CTAs)
+static int ring_dispatch(bool noise, bool src, const K2Params &p, const RingCfg &cfg, int slots, cudaStream_t st) {
     const void *fn = ring_fn(noise, src, cfg.npt);
-    int kb = cfg.kb;
+    int kb = cfg.kb, bands = cfg.bands;
+    if (cfg.band_nt > 0) {
+        void *args[] = {(void *)&p, (void *)&bands, (void *)&slots, (void *)&kb};
+        APDE_CUDA(cudaLaunchCooperativeKernel(fn, dim3(slots * bands), dim3(cfg.block), args, 0, st));
+        return APDE_OK;
+    }
     void *args2[] = {(void *)&p, (void *)&kb};
     void *args1[] = {(void *)&p};
-    APDE_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(cfg.block), cfg.npt > 0 ? args2 : args1, cfg.smem, st));
+    APDE_CUDA(cudaLaunchCooperativeKernel(fn, dim3(slots), dim3(cfg.block), cfg.npt > 0 ? args2 : args1, cfg.smem, st));
     return APDE_OK;
 }
 
@@ -721,7 +943,29 @@ static int ring_configure(bool noise, bool src, int64_t rows, int64_t cols, int6
     bool want2 = !noise && !many;
     if (force && !strcmp(force, "k2")) want2 = false;
     if (force && !strcmp(force, "k2b")) want2 = true;
-    if (can2 && want2) {
+    // K2c (row bands): the default wherever its ring of sweep slots can be made short enough for the width
+    // (slots * (3*kb + 4) <= cols, see the kernel) -- i.e. everything but very narrow grids
+    int band_kb = 4;
+    if (const char *v = getenv("APDE_BAND_KB")) band_kb = std::min(64, std::max(1, atoi(v)));
+    while (band_kb > 1 && cols < 3 * band_kb + 4) band_kb /= 2;
+    const bool can3 = cols >= 3 * band_kb + 4 && rows >= 3 && (rows + cols) * ((rows + 3) & ~(int64_t)3) < (1ll << 32);  // 32-bit element offsets
+    // measured on B200 (4096^2, 1 % mismatch, K=1000): 48 GLUP/s against K2's 86 -- one node per thread per step cannot
+    // amortise the ~100 instructions a step costs besides the node itself; opt-in only
+    bool want3 = false;
+    if (force) want3 = !strcmp(force, "band");
+    if (can3 && want3) {
+        int nt = rows - 2 >= 384 ? 512 : 256;
+        if (const char *v = getenv("APDE_BAND_NT")) {
+            const int b = atoi(v);
+            nt = b >= 512 ? 512 : (b >= 256 ? 256 : 64);
+        }
+        cfg->band_nt = nt;
+        cfg->block = nt;
+        cfg->npt = 1000 + nt;
+        cfg->kb = band_kb;
+        cfg->smem = 0;
+        cfg->bands = (int)((rows - 2 + nt - 1) / nt);
+    } else if (can2 && want2) {
         int block = 1024;
         while (block > 128 && block / 2 >= maxdiag) block /= 2;
         int npt = 1;
@@ -749,6 +993,15 @@ static int ring_configure(bool noise, bool src, int64_t rows, int64_t cols, int6
         return APDE_ECUDA;
     }
     cfg->grid_max = per_sm * prop.multiProcessorCount;
+    cfg->slots_max = cfg->grid_max;
+    if (cfg->band_nt > 0) {
+        cfg->slots_max = (int)std::min<int64_t>(cfg->grid_max / cfg->bands, cols / (3 * cfg->kb + 4));
+        if (cfg->slots_max < 1) {
+            set_error("exact band kernel: %d bands of %d rows exceed the %d co-resident CTAs", cfg->bands, cfg->band_nt,
+                      cfg->grid_max);
+            return APDE_EINVAL;
+        }
+    }
     return APDE_OK;
 }
 
@@ -790,8 +1043,8 @@ static int solve_ring(double *grid, const double *nh, const double *nv, const do
 
     RingCfg cfg;
     APDE_TRY(ring_configure(noise, has_src, rows, cols, max_iter, prop, &cfg));
-    const int gmax = cfg.grid_max;
-    APDE_TRY(d_prog.alloc((size_t)gmax * 16 * 8));
+    const int gmax = cfg.slots_max;  // sweeps in flight
+    APDE_TRY(d_prog.alloc((size_t)cfg.grid_max * 16 * 8));
 
     const bool may_stop = tol > 0.0;
     if (may_stop) APDE_TRY(snap.alloc(dbytes));
@@ -800,6 +1053,8 @@ static int solve_ring(double *grid, const double *nh, const double *nv, const do
     // fill/drain (2 diagonals per in-flight sweep) against nd diagonals per sweep
     int64_t chunk_cap = gmax;
     while (chunk_cap < 8 * (int64_t)gmax && (int64_t)(cfg.kb + 1) * chunk_cap > nd) chunk_cap *= 2;
+    // K2c: the fill is one band stagger per band plus a few steps per slot, a task is `cols` steps
+    if (cfg.band_nt > 0) chunk_cap = (int64_t)gmax * (cfg.bands > 2 ? 4 : 2);
 
     EventPair ev;
     APDE_TRY(ev.init());
@@ -825,6 +1080,7 @@ static int solve_ring(double *grid, const double *nh, const double *nv, const do
         if (may_stop) APDE_CUDA(cudaMemcpyAsync(snap.p, U.p, dbytes, cudaMemcpyDeviceToDevice, 0));
         APDE_CUDA(cudaMemsetAsync(d_prog.p, 0, d_prog.bytes, 0));
         p.hist = d_hist.as<double>() + done;
+        APDE_CUDA(cudaMemsetAsync(p.hist, 0, (size_t)chunk * 8, 0));  // K2c folds the residual with atomicMax
         p.n_sweeps = chunk;
         APDE_CUDA(cudaEventRecord(ev.a));
         APDE_TRY(ring_dispatch(noise, has_src, p, cfg, g, 0));
@@ -847,6 +1103,7 @@ static int solve_ring(double *grid, const double *nh, const double *nv, const do
                     // later sweeps of the chunk already ran: roll back, replay exactly stop+1 sweeps
                     APDE_CUDA(cudaMemcpyAsync(U.p, snap.p, dbytes, cudaMemcpyDeviceToDevice, 0));
                     APDE_CUDA(cudaMemsetAsync(d_prog.p, 0, d_prog.bytes, 0));
+                    APDE_CUDA(cudaMemsetAsync(p.hist, 0, (size_t)(stop + 1) * 8, 0));
                     p.n_sweeps = stop + 1;
                     APDE_CUDA(cudaEventRecord(ev.a));
                     APDE_TRY(ring_dispatch(noise, has_src, p, cfg, (int)std::min<int64_t>(stop + 1, gmax), 0));

@@ -474,7 +474,8 @@ __global__ void __launch_bounds__(PipeGeo<TD, NOISE>::NTHR, PipeGeo<TD, NOISE>::
 template <int TD, bool NOISE, bool SRC>
 int pipe_launch(apde_plan *p, const PipeArgs &a, cudaStream_t st) {
     using Geo_ = PipeGeo<TD, NOISE>;
-    static int per_sm = 0;
+    static int per_sm_dev[64] = {0};  // per device: the shared-memory opt-in belongs to one context
+    int &per_sm = per_sm_dev[p->device & 63];
     if (per_sm == 0) {
         int n = 0;
         APDE_CUDA(cudaFuncSetAttribute(rb_pipe_kernel<TD, NOISE, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo_::SMEM));

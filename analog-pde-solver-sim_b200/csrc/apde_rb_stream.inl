@@ -526,6 +526,11 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
 #pragma unroll
         for (int t = 0; t < TD; ++t) mxl[t] = (T)0;
 
+        // A steady-state copy of the loop body without the keep-the-old-value selects, the relaxed / counted bit tests
+        // and the store range test (interior strips, rows well inside the block) was built and measured in round 2:
+        // 643 instead of 830 instructions per two rows, and the same speed on every variant (fp64 Poisson 662 vs 674,
+        // fp32 1286 vs 1279, with conductances 425 / 893 vs 424 / 904 GLUP/s) -- the two resident warps per scheduler
+        // are bound by their dependent chains, not by issue slots.  Removed again.
         for (int rc = rs; rc <= r_last; rc += UNR) {
 #pragma unroll
             for (int rr = 0; rr < UNR; ++rr) {
@@ -780,7 +785,10 @@ int launch_pass(apde_plan *p, StreamArgs &a, const BlockReq &rq, cudaStream_t st
 #else
     constexpr size_t smem = rbs_ops((int)sizeof(T), C, NOISE) ? (size_t)(RBS_THREADS / 32) * rbs_ops_warp_bytes(C * (int)sizeof(T), TD, SRC, NOISE) : 0;
 #endif
-    static int blocks_per_sm = 0;
+    // per device: the dynamic shared-memory opt-in is an attribute of the function IN ONE CONTEXT (a second GPU of the
+    // same process -- apde_solve_redblack_multi -- needs its own call, or its launches fail with "invalid argument")
+    static int blocks_per_sm_dev[64] = {0};
+    int &blocks_per_sm = blocks_per_sm_dev[p->device & 63];
     if (blocks_per_sm == 0) {
         int n = 0;
         if (smem > 48 * 1024)

@@ -3,6 +3,7 @@ the reference's surface; nothing in the product imports the oracle; no silent CP
 import inspect
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -165,3 +166,21 @@ def test_environment_options_are_validated(monkeypatch):
         with pytest.raises(ValueError, match=name if name != "APDE_MODE" else "fastest"):
             d.solve(lambda i, j, r, c: 1.0 if i == 0 else None, mode=None if name == "APDE_MODE" else "redblack")
         monkeypatch.delenv(name)
+
+
+def test_band_kernel_flag_protocol_never_deadlocks():
+    """The exact path's row-band kernel (K2c) is a cooperative kernel whose CTAs wait for each other: a launch shape
+    that can deadlock would hang the GPU.  tools/band_protocol_sim.py replays the flag protocol on the CPU with the
+    launch shape the host picks (slots * (3*kb + 4) <= cols): nothing may be left unfinished -- and the first version
+    of the protocol (progress withheld while a CTA polls) is shown to deadlock on the shape that exposed it."""
+    import random
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import band_protocol_sim as sim
+    rng = random.Random(7)
+    for _ in range(60):
+        nt, kb = rng.choice([64, 256, 512]), rng.choice([1, 2, 4, 8, 16])
+        rows, cols, k = rng.randint(3, 1200), rng.randint(3 * kb + 4, 400), rng.randint(1, 80)
+        assert sim.replay(rows, cols, nt, kb, k) == [], (rows, cols, nt, kb, k)
+    for shape in ((67, 300, 64, 8, 90), (200, 130, 64, 4, 150), (131, 90, 64, 1, 77), (1100, 520, 512, 4, 45)):
+        assert sim.replay(*shape) == [], shape
+    assert sim.replay(67, 300, 64, 8, 90, publish_first=False, slots=15) != []

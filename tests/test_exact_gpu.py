@@ -11,6 +11,18 @@ from analog_pde_solver import AnalogPDESolver, DigitalSolver, EnergyModel, _back
 pytestmark = pytest.mark.gpu
 
 
+def _force_ring_kernel(path, monkeypatch):
+    """'ring-k2' / 'ring-k2b' / 'ring-band<rows per band>' -> env for the kernel choice, returns the exact_path."""
+    if not path.startswith("ring-"):
+        return path
+    kern = path[5:]
+    if kern.startswith("band"):
+        monkeypatch.setenv("APDE_BAND_NT", kern[4:])  # 64-row bands: several bands and sweep slots on small grids
+        kern = "band"
+    monkeypatch.setenv("APDE_RING_KERNEL", kern)
+    return "ring"
+
+
 def _solve(c, path):
     g = c["grid0"].copy()
     hist, n, ksec = _backend.solve("exact", g, c["noise_h"], c["noise_v"], c["source"], c["tol"],
@@ -27,12 +39,13 @@ def test_golden_bit_exact_auto_path(golden, name):
     assert g.tobytes() == c["solution"].tobytes()
 
 
+@pytest.mark.parametrize("kern", ["default", "ring-k2", "ring-band64"])
 @pytest.mark.parametrize("name", [n for n in GOLDEN_NAMES if n not in ("rows2", "cols1")])
-def test_golden_bit_exact_ring_path(golden, name):
-    """Force the multi-CTA ring kernel on every case, including the ones that fit one CTA;
+def test_golden_bit_exact_ring_path(golden, name, kern, monkeypatch):
+    """Force the multi-CTA kernels on every case, including the ones that fit one CTA;
     the early-stop cases exercise snapshot / rollback / replay."""
     c = golden.case(name)
-    g, hist, n = _solve(c, "ring")
+    g, hist, n = _solve(c, "ring" if kern == "default" else _force_ring_kernel(kern, monkeypatch))
     assert n == c["iters"]
     assert hist.tobytes() == c["hist"].tobytes()
     assert g.tobytes() == c["solution"].tobytes()
@@ -64,11 +77,9 @@ def test_python_classes_reproduce_reference(golden, name):
     (33, 65, 0.01, True, 40), (65, 33, 0.0, True, 40), (70, 70, 0.03, False, 31),
     (257, 129, 0.01, True, 11), (300, 300, 0.0, False, 13), (513, 700, 0.01, True, 6),
 ])
-@pytest.mark.parametrize("path", ["auto", "ring", "ring-k2", "ring-k2b"])
+@pytest.mark.parametrize("path", ["auto", "ring", "ring-k2", "ring-k2b", "ring-band64", "ring-band256", "ring-band512"])
 def test_fixed_sweeps_vs_oracle(rows, cols, sigma, src, k, path, monkeypatch):
-    if path.startswith("ring-"):  # both ring kernels on every shape (default picks one per problem)
-        monkeypatch.setenv("APDE_RING_KERNEL", path[5:])
-        path = "ring"
+    path = _force_ring_kernel(path, monkeypatch)  # every ring kernel on every shape (default picks one per problem)
     g0, nh, nv, s = random_problem(rows, cols, sigma, seed=rows * 1000 + cols, with_source=src)
     ru, rh, rn = oracle.gauss_seidel(g0, nh, nv, s, 0.0, k)
     g = g0.copy()
@@ -78,12 +89,10 @@ def test_fixed_sweeps_vs_oracle(rows, cols, sigma, src, k, path, monkeypatch):
     assert g.tobytes() == ru.tobytes()
 
 
-@pytest.mark.parametrize("path", ["small", "ring", "ring-k2", "ring-k2b"])
+@pytest.mark.parametrize("path", ["small", "ring", "ring-k2", "ring-k2b", "ring-band64"])
 @pytest.mark.parametrize("tol", [1e-3, 1e-5, 3e-7])
 def test_early_stop_at_first_crossing(path, tol, monkeypatch):
-    if path.startswith("ring-"):
-        monkeypatch.setenv("APDE_RING_KERNEL", path[5:])
-        path = "ring"
+    path = _force_ring_kernel(path, monkeypatch)
     """Stops at the true first sweep with max_change < tol although later sweeps were already in
     flight (snapshot + replay)."""
     g0, nh, nv, s = random_problem(40, 36, 0.01, seed=77)
@@ -91,6 +100,27 @@ def test_early_stop_at_first_crossing(path, tol, monkeypatch):
     g = g0.copy()
     hist, n, _ = _backend.solve("exact", g, nh, nv, s, tol, 20000, exact_path=path)
     assert n == rn and hist.tobytes() == rh.tobytes() and g.tobytes() == ru.tobytes()
+
+
+@pytest.mark.parametrize("rows,cols,nt,kb,k", [
+    (200, 130, 64, 4, 150),    # 4 bands, 10 sweep slots: 15 rounds through the ring of slots
+    (131, 90, 64, 1, 77),      # progress exchanged every step; last band 1 row short of full
+    (67, 300, 64, 8, 90),      # 2 bands, the second with a single row (its thread is first AND last row)
+    (600, 257, 256, 4, 61),    # 3 bands of 256
+    (1100, 520, 512, 4, 45),   # 3 bands of 512, two CTAs per SM
+])
+@pytest.mark.parametrize("sigma,src", [(0.01, True), (0.0, False)])
+def test_band_kernel_ring_of_slots_wraps(rows, cols, nt, kb, k, sigma, src, monkeypatch):
+    """K2c with more sweeps than sweep slots: every CTA runs several tasks back to back, threads of one CTA are on
+    different sweeps at the same time, and slot 0 follows slot Gs-1 of the previous round."""
+    monkeypatch.setenv("APDE_RING_KERNEL", "band")
+    monkeypatch.setenv("APDE_BAND_NT", str(nt))
+    monkeypatch.setenv("APDE_BAND_KB", str(kb))
+    g0, nh, nv, s = random_problem(rows, cols, sigma, seed=rows + cols, with_source=src)
+    ru, rh, rn = oracle.gauss_seidel_mt(g0, nh, nv, s, k)
+    g = g0.copy()
+    hist, n, _ = _backend.solve("exact", g, nh, nv, s, 0.0, k, exact_path="ring")
+    assert n == k and hist.tobytes() == rh.tobytes() and g.tobytes() == ru.tobytes()
 
 
 def test_ring_kernel_medium_grid_with_stop():
@@ -202,11 +232,17 @@ def test_unsafe_links_take_the_general_division():
     nh[9, 9] = np.nextafter(1.0, 0.0)
     g0[10, 10] = -0.0
     g0[11, 3] = 5e-324
-    for path in ("small", "ring"):
-        ru, rh, rn = oracle.gauss_seidel(g0, nh, nv, s, 0.0, 12)
-        g = g0.copy()
-        hist, n, _ = _backend.solve("exact", g, nh, nv, s, 0.0, 12, exact_path=path)
-        assert g.tobytes() == ru.tobytes() and hist.tobytes() == rh.tobytes()
+    import os
+    for path, kern in (("small", None), ("ring", "k2"), ("ring", "band")):
+        if kern:
+            os.environ["APDE_RING_KERNEL"] = kern
+        try:
+            ru, rh, rn = oracle.gauss_seidel(g0, nh, nv, s, 0.0, 12)
+            g = g0.copy()
+            hist, n, _ = _backend.solve("exact", g, nh, nv, s, 0.0, 12, exact_path=path)
+        finally:
+            os.environ.pop("APDE_RING_KERNEL", None)
+        assert g.tobytes() == ru.tobytes() and hist.tobytes() == rh.tobytes(), (path, kern)
 
 
 def test_config3_size_4096_mismatch_iterates():
