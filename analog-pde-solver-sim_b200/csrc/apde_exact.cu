@@ -36,9 +36,11 @@ namespace apde {
 //
 // A link is stored as {b, y}: b = the reference's mismatch factor, y = RN(1/b) computed once at
 // upload (__drcp_rn, correctly rounded) or 0.0 when b is not "safe" (see link_reciprocal).
-// For |a| in [2^-700, 2^700]:
+// For |a| in [2^-900, 2^900] (round 2: was 2^+-700; a field decaying away from a hot edge spends ~4 binades per row,
+// so the wider window moves 50 more rows of a 4096^2 grid off the general division):
 //     q0 = RN(a*y)                 within 1.5 ulp of a/b (y has relative error <= 2^-53)
-//     r0 = fma(-q0, b, a)          exact (fits 53 bits, cannot underflow in the screened ranges)
+//     r0 = fma(-q0, b, a)          exact: fits 53 bits, and its last bit has exponent >= e_a - 104 >= -1004 > -1074 while
+//                                  |q0| >= 2^-900 * 2^-100 stays normal for the screened links |b| in [2^-100, 2^100]
 //     q1 = fma(r0, y, q0)          = RN(a/b + (r0/b)*eps): faithful
 //     r1 = fma(-q1, b, a)          exact
 //     q2 = fma(r1, y, q1)          = RN(a/b + (r1/b)*eps) = RN(a/b)   (Markstein's theorem: holds for a
@@ -60,7 +62,7 @@ __device__ __forceinline__ double exact_div(double a, double2 link) {
     if (y != 0.0) {
         const unsigned hi = (unsigned)__double2hiint(a);
         const unsigned e = (hi >> 20) & 0x7ffu;
-        if ((e - 323u) <= 1400u) {  // |a| in [2^-700, 2^700]
+        if ((e - 123u) <= 1800u) {  // |a| in [2^-900, 2^900]
             double q = __dmul_rn(a, y);
             double r = __fma_rn(-q, b, a);
             q = __fma_rn(r, y, q);
@@ -76,15 +78,60 @@ __device__ __forceinline__ double exact_div(double a, double2 link) {
 // ------------------------------------------------------------------------------------------
 // the node update, shared by K1 and K2
 // ------------------------------------------------------------------------------------------
+// Branch-free form of exact_div: the quotient of the screened fast path, or the correctly signed zero, selected by
+// predicates; anything else (unscreened link, tiny / huge / non-finite numerator) raises `slow` and the caller redoes
+// the node with the general division.  No branch per division, so the four divisions of a node interleave in the fp64
+// pipe instead of running one behind the other.
+__device__ __forceinline__ double band_div(double a, double2 link, bool &slow) {
+    const double b = link.x, y = link.y;
+    const unsigned hi = (unsigned)__double2hiint(a);
+    const bool inr = ((hi & 0x7ff00000u) - (123u << 20)) <= (1800u << 20);  // |a| in [2^-900, 2^900]
+    double q = __dmul_rn(a, y);
+    double r = __fma_rn(-q, b, a);
+    q = __fma_rn(r, y, q);
+    r = __fma_rn(-q, b, a);
+    q = __fma_rn(r, y, q);
+    const double z = __hiloint2double((int)((hi ^ (unsigned)__double2hiint(b)) & 0x80000000u), 0);
+    slow = slow || (y == 0.0) || !(inr || a == 0.0);
+    return inr ? q : z;
+}
+
+// the node with four general IEEE divisions (what exact_div falls back to; same bits by construction), out of line so
+// that the rare path costs the hot loop no registers
+template <bool HAS_SRC>
+__device__ __noinline__ double relax_node_general(double un, double us, double uw, double ue, double bn, double bs, double bw,
+                                                  double be, double src) {
+    double acc = __dadd_rn(__ddiv_rn(un, bn), __ddiv_rn(us, bs));
+    acc = __dadd_rn(acc, __ddiv_rn(uw, bw));
+    acc = __dadd_rn(acc, __ddiv_rn(ue, be));
+    if (HAS_SRC) acc = __dsub_rn(acc, src);
+    return __dmul_rn(acc, 0.25);
+}
+
+// R = rows per thread ("walkers"): thread r owns rows r, r + NT, ..., r + (R-1)*NT of the band (band height H = R*NT);
+// walker k of thread r is the band's virtual thread v = k*NT + r and runs v steps behind virtual thread 0, so the R
+// nodes a thread relaxes in one step are independent of each other (instruction-level parallelism across the four
+// divisions x R nodes) and share the step's barrier, flag exchange and loop bookkeeping.
 template <bool HAS_NOISE, bool HAS_SRC>
 __device__ __forceinline__ double relax_node(double un, double us, double uw, double ue,
                                              double2 ln, double2 ls, double2 lw, double2 le,
                                              double src) {
     if (HAS_NOISE) {
+#ifndef APDE_BRANCHY_DIV
+        bool slow = false;
+        const double qn = band_div(un, ln, slow), qs = band_div(us, ls, slow);  // solver.py:269-270
+        const double qw = band_div(uw, lw, slow), qe = band_div(ue, le, slow);  // :271-272
+        if (slow) return relax_node_general<HAS_SRC>(un, us, uw, ue, ln.x, ls.x, lw.x, le.x, src);  // rare, out of line
+        un = qn;
+        us = qs;
+        uw = qw;
+        ue = qe;
+#else
         un = exact_div(un, ln);  // solver.py:269
         us = exact_div(us, ls);  // :270
         uw = exact_div(uw, lw);  // :271
         ue = exact_div(ue, le);  // :272
+#endif
     }
     double acc = __dadd_rn(un, us);  // :275, left-associative
     acc = __dadd_rn(acc, uw);
@@ -125,6 +172,7 @@ __global__ void division_selftest_kernel(long long n, unsigned long long seed, u
         if (mode == 2) sig = 0xFFFFFFFFFFFFFull - ((rc >> 40) & 0xFFFFF);
         long long eb = 1023 + (long long)((rc >> 8) % 5) - 2;           // 2^-2 .. 2^2
         if (mode == 3) eb = 1023 + (long long)((rc >> 8) % 300) - 150;  // includes unscreened exponents
+        if (mode == 4) eb = 1023 + (((rc >> 8) & 1) ? 97 : -100) + (long long)((rc >> 9) % 4);  // the ends of the screen
         const unsigned long long sb = (rc >> 7) & 1ull;
         const double b = __longlong_as_double((long long)((sb << 63) | ((unsigned long long)eb << 52) | sig));
         // numerator: mostly mid-range, some tiny / huge / zero / subnormal / inf / nan
@@ -135,7 +183,9 @@ __global__ void division_selftest_kernel(long long n, unsigned long long seed, u
         else if (ma == 2) a = __longlong_as_double((long long)(ra & 0x800FFFFFFFFFFFFFull));  // subnormal
         else if (ma == 3) a = __longlong_as_double((long long)ra);                              // any bits
         else {
-            long long ea = 1023 + (long long)((ra >> 53) % 1500) - 750;
+            long long ea = 1023 + (long long)((ra >> 53) % 2040) - 1020;  // both sides of the 2^+-900 screen
+            if (ma == 5) ea = 1023 - 904 + (long long)((ra >> 53) % 8);  // around the lower end of the numerator window
+            if (ma == 6) ea = 1023 + 896 + (long long)((ra >> 53) % 8);  // around the upper end
             if (ma >= 8) ea = 1023 + (long long)((ra >> 53) % 40) - 20;
             a = __longlong_as_double((long long)((ra & 0x800FFFFFFFFFFFFFull) | ((unsigned long long)ea << 52)));
         }
@@ -143,6 +193,9 @@ __global__ void division_selftest_kernel(long long n, unsigned long long seed, u
         const double fast = exact_div(a, link), ref = __ddiv_rn(a, b);
         const bool same = (__double_as_longlong(fast) == __double_as_longlong(ref)) || (fast != fast && ref != ref);
         if (!same) ++bad;
+        bool slow = false;  // the branch-free form: whatever it does not hand to the general division must be right
+        const double bq = band_div(a, link, slow);
+        if (!slow && __double_as_longlong(bq) != __double_as_longlong(ref)) ++bad;
     }
     if (bad) atomicAdd(mismatches, bad);
 }
@@ -603,38 +656,33 @@ __global__ void __launch_bounds__(1024, 1) exact_ring2_kernel(K2Params p, int kb
 // Gs * (3*kb + 4) <= cols (tools/band_protocol_sim.py replays the protocol on the CPU).  One __syncthreads per step
 // (north hand-off between warps), one more where progress is published.
 // ------------------------------------------------------------------------------------------
-// Branch-free form of exact_div for the band kernel: the quotient of the screened fast path, or the correctly signed
-// zero, selected by predicates; anything else (unscreened link, tiny / huge / non-finite numerator) raises `slow` and
-// the caller redoes the node with the general division.  No branch per division, so the four divisions of a node
-// interleave in the fp64 pipe instead of running one behind the other.
-__device__ __forceinline__ double band_div(double a, double2 link, bool &slow) {
-    const double b = link.x, y = link.y;
-    const unsigned hi = (unsigned)__double2hiint(a);
-    const bool inr = ((hi & 0x7ff00000u) - (323u << 20)) <= (1400u << 20);  // |a| in [2^-700, 2^700]
-    double q = __dmul_rn(a, y);
-    double r = __fma_rn(-q, b, a);
-    q = __fma_rn(r, y, q);
-    r = __fma_rn(-q, b, a);
-    q = __fma_rn(r, y, q);
-    const double z = __hiloint2double((int)((hi ^ (unsigned)__double2hiint(b)) & 0x80000000u), 0);
-    slow = slow || (y == 0.0) || !(inr || a == 0.0);
-    return inr ? q : z;
-}
+// LPF: the links and the source value of the NEXT step are requested into registers together with its east operand
+// (12-14 more registers per walker), so no load of the current step is ever waited for; without it they are read in
+// the step itself behind an L1 prefetch.  Either way every thread pulls its operand lines of the step L2AHEAD steps
+// ahead from HBM into L2: the first sweep to reach a diagonal (its links were evicted since the previous round) would
+// otherwise pay a DRAM round trip in every step, and every other sweep in flight is rate-locked to it.
+#ifndef APDE_BAND_L2AHEAD
+#define APDE_BAND_L2AHEAD 12
+#endif
+__device__ __forceinline__ void prefetch_l2_line(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// the node with four general IEEE divisions (what exact_div falls back to; same bits by construction), out of line so
-// that the rare path costs the hot loop no registers
-template <bool HAS_SRC>
-__device__ __noinline__ double relax_node_general(double un, double us, double uw, double ue, double bn, double bs, double bw,
-                                                  double be, double src) {
-    double acc = __dadd_rn(__ddiv_rn(un, bn), __ddiv_rn(us, bs));
-    acc = __dadd_rn(acc, __ddiv_rn(uw, bw));
-    acc = __dadd_rn(acc, __ddiv_rn(ue, be));
-    if (HAS_SRC) acc = __dsub_rn(acc, src);
-    return __dmul_rn(acc, 0.25);
-}
+// Operands of one step that come from global memory, requested one step ahead.  The kernel keeps TWO of these and
+// alternates them between consecutive steps (the loop body is instantiated twice), so a request never has to be
+// moved to another register: it stays in flight across the step's barrier and is first waited for where the next step
+// uses it.  (A single set rotated with moves at the end of the step made every step wait for its own requests -- a
+// full L2 / DRAM round trip per step, 2.5 us per step even on an otherwise idle SM.)
+template <int R, bool LPF>
+struct BandOperands {
+    double ue[R];               // east operand u_{t-1}(i, j+1)
+    double us[R];               // south operand from memory: lane 31 and the band's last row
+    double un0;                 // north operand of the band's first row
+    double2 le[LPF ? R : 1], ls[LPF ? R : 1], ln[LPF ? R : 1];  // east / south / north link of the node
+    double sv[LPF ? R : 1];     // source value
+};
 
-template <bool HAS_NOISE, bool HAS_SRC, int NT, int MINB>
+template <bool HAS_NOISE, bool HAS_SRC, int NT, int R, int MINB, bool LPF>
 __global__ void __launch_bounds__(NT, MINB) exact_band_kernel(K2Params p, int B, int Gs, int kb) {
+    constexpr int H = R * NT, NWARP = NT / 32;
     const int rows = p.rows, cols = p.cols;
     const unsigned P = (unsigned)p.P;  // element offsets fit 32 bits (checked by the host): one IMAD.WIDE per address
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -643,13 +691,11 @@ __global__ void __launch_bounds__(NT, MINB) exact_band_kernel(K2Params p, int B,
     const int ntasks = (int)((p.n_sweeps - slot + Gs - 1) / Gs);  // the launch guarantees slot < n_sweeps
     const int pslot = slot == 0 ? Gs - 1 : slot - 1;
     const int ntasks_p = (int)((p.n_sweeps - pslot + Gs - 1) / Gs);
-    const int i0 = 1 + band * NT;
-    const int rows_b = min(NT, rows - 1 - i0);  // rows of this band (>= 1)
-    const int i = i0 + tid;
-    const bool row_ok = tid < rows_b;
-    const bool sx = row_ok && (lane == 31 || tid == rows_b - 1);  // south operand comes from memory
-    const long long Stot = (long long)ntasks * CP + NT - 1, totP = (long long)ntasks_p * CP + NT - 1;
-    __shared__ double nbuf[2][NT / 32];
+    const int i0 = 1 + band * H;
+    const int rows_b = min(H, rows - 1 - i0);  // rows of this band (>= 1)
+    const long long Stot = (long long)ntasks * CP + H - 1, totP = (long long)ntasks_p * CP + H - 1;
+    // north hand-off between neighbouring virtual threads that are not neighbouring lanes: [parity][walker][warp]
+    __shared__ double nbuf[2][R][NWARP];  // lane 31's result of the step
     double *__restrict__ U = p.U;
     const double2 *__restrict__ LH = p.LH, *__restrict__ LV = p.LV;
     const double *__restrict__ SRC = p.S;
@@ -666,29 +712,55 @@ __global__ void __launch_bounds__(NT, MINB) exact_band_kernel(K2Params p, int B,
         }
         if (tid == 1 && band + 1 < B) {
             f_ptr = p.progress + ((size_t)pslot * B + band + 1) * 16;
-            f_add = 2 - NT - adj;
+            f_add = 2 - H - adj;
             f_cap = totP;
         }
         if (tid == 2 && band > 0) {
             f_ptr = p.progress + ((size_t)slot * B + band - 1) * 16;
-            f_add = NT;
+            f_add = H;
             f_cap = Stot;
         }
     }
     unsigned long long *fme = p.progress + (size_t)blockIdx.x * 16;
 
-    const unsigned off0 = (unsigned)(i - 1) * P + (unsigned)i;  // node (i, -1)
-    unsigned off = off0;
-    int n = 0;
-    int jx = -tid;  // column jx - 1; negative: the row has not started yet
-    double uw = 0.0, old = 0.0, mx = 0.0, ue_c = 0.0, us_c = 0.0, un_c = 0.0;
-    double2 lw = make_double2(1.0, 1.0);
-    if (tid == 0 && ntasks > 0) ue_c = __ldcg(U + off0 + P);  // u(i,0), a ring value
+    // the west link: carried in registers from the previous step (R <= 2) or re-read (an L1 hit: it was the east link
+    // one step ago) where four walkers leave no registers for it
+    constexpr bool LWREG = R <= 2;
+    const unsigned off00 = (unsigned)(i0 + tid - 1) * P + (unsigned)(i0 + tid);  // node (i, -1) of walker 0
+    unsigned off[R];
+    int jx[R], n[R];
+    double uw[R], old[R], mx[R];
+    double2 lw[LWREG ? R : 1];
+#define OFF0(k) (off00 + (unsigned)((k) * NT) * (P + 1u))
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        off[k] = OFF0(k);
+        jx[k] = -(k * NT + tid);  // column jx - 1; negative: the row has not started yet
+        n[k] = 0;
+        uw[k] = old[k] = mx[k] = 0.0;
+        if (LWREG) lw[k] = make_double2(1.0, 1.0);
+    }
+    const int v_last = rows_b - 1;  // the band's last row: its south operand comes from memory
+    BandOperands<R, LPF> opA, opB;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        opA.ue[k] = opA.us[k] = opB.ue[k] = opB.us[k] = 0.0;
+        if (LPF) {
+            opA.le[k] = opA.ls[k] = opA.ln[k] = opB.le[k] = opB.ls[k] = opB.ln[k] = make_double2(1.0, 1.0);
+            opA.sv[k] = opB.sv[k] = 0.0;
+        }
+    }
+    opA.un0 = opB.un0 = 0.0;
+    if (tid == 0 && ntasks > 0) opA.ue[0] = __ldcg(U + off00 + P);  // u(i,0), a ring value
 
     int kbc = 0;
     unsigned par = 0;  // S & 1
-    for (long long S = 0; S < Stot; ++S) {
-        if (kbc == 0) {
+    long long S = 0;
+    // one step: consumes `cur` (requested during the previous step), requests `nxt`
+    const bool nosync = kb < 0;  // timing experiment only (APDE_BAND_NOSYNC): no flag exchange, results are garbage
+    if (nosync) kb = -kb;
+    auto step = [&](BandOperands<R, LPF> &cur, BandOperands<R, LPF> &nxt) {
+        if (kbc == 0 && !nosync) {
             // publish BEFORE polling: a CTA that is waiting for its predecessors must not withhold the steps it has
             // already completed from its successors (withholding adds kb steps of lag per hop around the ring of
             // slots -- measured as a deadlock at 15 slots x kb 8 on 300 columns)
@@ -706,77 +778,116 @@ __global__ void __launch_bounds__(NT, MINB) exact_band_kernel(K2Params p, int B,
         __syncthreads();
         if (++kbc == kb) kbc = 0;
 
-        // ---- the thread's next step, and the u operands it will need (one step of cover for the L2 round trip)
-        int jxn = jx + 1, nn = n;
-        unsigned offn = jx >= 0 ? off + P : off0;
-        if (jxn == CP) {
-            jxn = 0;
-            offn = off0;
-            nn = n + 1;
-        }
-        const bool actn = row_ok && jxn >= 0 && nn < ntasks;
-        double ue_n = 0.0, us_n = 0.0, un_n = 0.0;
-        if (actn) {
-            ue_n = __ldcg(U + (offn + P));
-            if (jxn >= 2) {
-                if (sx) us_n = __ldcg(U + (offn + P + 1u));
-                if (tid == 0) un_n = __ldcg(U + (offn - P - 1u));
-                if (HAS_NOISE) {
-                    prefetch_l1_line(LV + offn);
-                    prefetch_l1_line(LH + offn);
+        // ---- every walker's next step, and the operands it will need
+        int jxn[R], nn[R];
+        unsigned offn[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const int v = k * NT + tid;
+            jxn[k] = jx[k] + 1;
+            nn[k] = n[k];
+            offn[k] = jx[k] >= 0 ? off[k] + P : OFF0(k);
+            if (jxn[k] == CP) {
+                jxn[k] = 0;
+                offn[k] = OFF0(k);
+                nn[k] = n[k] + 1;
+            }
+            if (v < rows_b && jxn[k] >= 0 && nn[k] < ntasks) {
+                nxt.ue[k] = __ldcg(U + (offn[k] + P));
+                if (LPF && HAS_NOISE && jxn[k] >= 1) nxt.le[k] = __ldg(LH + offn[k]);
+                if (jxn[k] >= 2) {
+                    if (lane == 31 || v == v_last) nxt.us[k] = __ldcg(U + (offn[k] + P + 1u));
+                    if (k == 0 && tid == 0) nxt.un0 = __ldcg(U + (offn[k] - P - 1u));
+                    if (LPF) {
+                        if (HAS_NOISE) {
+                            nxt.ls[k] = __ldg(LV + offn[k]);
+                            nxt.ln[k] = __ldg(LV + (offn[k] - P - 1u));
+                        }
+                        if (HAS_SRC) nxt.sv[k] = __ldg(SRC + offn[k]);
+                    } else {
+                        if (HAS_NOISE) {
+                            prefetch_l1_line(LV + offn[k]);
+                            prefetch_l1_line(LH + offn[k]);
+                        }
+                        if (HAS_SRC) prefetch_l1_line(SRC + offn[k]);
+                    }
                 }
-                if (HAS_SRC) prefetch_l1_line(SRC + offn);
+                if (APDE_BAND_L2AHEAD > 0 && (HAS_NOISE || HAS_SRC)) {
+                    // same row, L2AHEAD columns on (past the row's end: padding or the first diagonals below, harmless)
+                    const unsigned oa = offn[k] + (unsigned)APDE_BAND_L2AHEAD * P;
+                    if (HAS_NOISE) {
+                        prefetch_l2_line(LV + oa);
+                        prefetch_l2_line(LH + oa);
+                    }
+                    if (HAS_SRC) prefetch_l2_line(SRC + oa);
+                }
             }
         }
         // ---- this step
-        const bool act = row_ok && jx >= 0 && n < ntasks;
-        double us = __shfl_down_sync(0xffffffffu, ue_c, 1);
-        double un = __shfl_up_sync(0xffffffffu, uw, 1);
-        if (sx) us = us_c;
-        if (lane == 0) un = (tid == 0) ? un_c : nbuf[par ^ 1u][warp > 0 ? warp - 1 : 0];  // written in step S-1
-        double val = old;  // the boundary column passes through
-        double2 le = make_double2(1.0, 1.0);
-        if (act && jx >= 1) {
-            if (HAS_NOISE) le = __ldg(LH + off);
-            if (jx >= 2) {
-                double sv = 0.0;
-                if (HAS_SRC) sv = __ldg(SRC + off);
-                if (HAS_NOISE) {
-                    const double2 ln = __ldg(LV + (off - P - 1u)), ls = __ldg(LV + off);
-                    bool slow = false;
-                    const double qn = band_div(un, ln, slow), qs = band_div(us, ls, slow);
-                    const double qw = band_div(uw, lw, slow), qe = band_div(ue_c, le, slow);
-                    double acc = __dadd_rn(__dadd_rn(__dadd_rn(qn, qs), qw), qe);  // solver.py:275, left-associative
-                    if (HAS_SRC) acc = __dsub_rn(acc, sv);
-                    val = __dmul_rn(acc, 0.25);
-                    if (slow) val = relax_node_general<HAS_SRC>(un, us, uw, ue_c, ln.x, ls.x, lw.x, le.x, sv);
-                } else {
-                    val = relax_node<false, HAS_SRC>(un, us, uw, ue_c, le, le, le, le, sv);
-                }
-                mx = max_ignore_nan(mx, fabs(__dsub_rn(val, old)));
-                __stcg(U + off, val);
-                if (jx == CP - 1) {  // end of the row: this sweep's residual (solver.py:277-281)
-                    atomic_max_nonneg(p.hist + (slot + (long long)n * Gs), mx);
-                    mx = 0.0;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const int v = k * NT + tid;
+            const bool act = v < rows_b && jx[k] >= 0 && n[k] < ntasks;
+            double us = __shfl_down_sync(0xffffffffu, cur.ue[k], 1);
+            double un = __shfl_up_sync(0xffffffffu, uw[k], 1);
+            if (lane == 31 || v == v_last) us = cur.us[k];
+            if (lane == 0) {
+                if (warp > 0) un = nbuf[par ^ 1u][k][warp > 0 ? warp - 1 : 0];
+                else if (k > 0) un = nbuf[par ^ 1u][k > 0 ? k - 1 : 0][NWARP - 1];
+                else un = cur.un0;
+            }
+            double val = old[k];  // the boundary column passes through
+            double2 le = make_double2(1.0, 1.0);
+            if (act && jx[k] >= 1) {
+                const unsigned o = off[k];
+                if (LPF) le = cur.le[LPF ? k : 0];
+                else if (HAS_NOISE && (LWREG || jx[k] >= 2)) le = __ldg(LH + o);
+                if (jx[k] >= 2) {
+                    double sv = 0.0;
+                    if (LPF) sv = cur.sv[LPF ? k : 0];
+                    else if (HAS_SRC) sv = __ldg(SRC + o);
+                    if (HAS_NOISE) {
+                        const double2 ln = LPF ? cur.ln[LPF ? k : 0] : __ldg(LV + (o - P - 1u));
+                        const double2 ls = LPF ? cur.ls[LPF ? k : 0] : __ldg(LV + o);
+                        const double2 lwk = LWREG ? lw[LWREG ? k : 0] : __ldg(LH + (o - P));
+                        bool slow = false;
+                        const double qn = band_div(un, ln, slow), qs = band_div(us, ls, slow);
+                        const double qw = band_div(uw[k], lwk, slow), qe = band_div(cur.ue[k], le, slow);
+                        double acc = __dadd_rn(__dadd_rn(__dadd_rn(qn, qs), qw), qe);  // solver.py:275, left-associative
+                        if (HAS_SRC) acc = __dsub_rn(acc, sv);
+                        val = __dmul_rn(acc, 0.25);
+                        if (slow) val = relax_node_general<HAS_SRC>(un, us, uw[k], cur.ue[k], ln.x, ls.x, lwk.x, le.x, sv);
+                    } else {
+                        val = relax_node<false, HAS_SRC>(un, us, uw[k], cur.ue[k], le, le, le, le, sv);
+                    }
+                    mx[k] = max_ignore_nan(mx[k], fabs(__dsub_rn(val, old[k])));
+                    __stcg(U + o, val);
+                    if (jx[k] == CP - 1) {  // end of the row: this sweep's residual (solver.py:277-281)
+                        atomic_max_nonneg(p.hist + (slot + (long long)n[k] * Gs), mx[k]);
+                        mx[k] = 0.0;
+                    }
                 }
             }
+            if (act) {
+                uw[k] = val;
+                old[k] = cur.ue[k];
+                if (LWREG) lw[LWREG ? k : 0] = le;
+            }
+            if (lane == 31) nbuf[par][k][warp] = uw[k];
+            jx[k] = jxn[k];
+            off[k] = offn[k];
+            n[k] = nn[k];
         }
-        if (act) {
-            uw = val;
-            old = ue_c;
-            lw = le;
-        }
-        if (lane == 31) nbuf[par][warp] = uw;
         par ^= 1u;
-        jx = jxn;
-        off = offn;
-        n = nn;
-        ue_c = ue_n;
-        us_c = us_n;
-        un_c = un_n;
+        ++S;
+    };
+    while (S < Stot) {
+        step(opA, opB);
+        if (S < Stot) step(opB, opA);
     }
     __syncthreads();
     if (tid == NT - 1) st_release_u64(fme, (unsigned long long)Stot);
+#undef OFF0
 }
 
 // ------------------------------------------------------------------------------------------
@@ -880,7 +991,8 @@ struct RingCfg {
     int kb = 8;        // diagonals per progress exchange (K2b) / steps per progress exchange (K2c)
     size_t smem = 0;
     int grid_max = 0;  // co-resident CTAs
-    int band_nt = 0;   // > 0: K2c (row bands) with this many rows per band
+    int band_nt = 0;   // > 0: K2c (row bands) with this many threads per CTA ...
+    int band_r = 1;    // ... and rows per thread (band height = band_nt * band_r)
     int bands = 1;     // K2c: CTAs per sweep
     int slots_max = 0; // sweeps in flight at most (K2/K2b: grid_max)
 };
@@ -892,9 +1004,16 @@ static const void *ring_fn(int npt) {
     // beat the 128-register shapes with four nodes in flight (256 x 2: 71; 512 x 1: 62 / 43) -- more warps hide the
     // L2 latency better than more loads per warp; without links four nodes in flight fit 64 registers: 165 -> 205.
     switch (npt) {
-        case 1064: return (const void *)exact_band_kernel<N, S, 64, 8>;  // K2c: 1000 + rows per band
-        case 1256: return (const void *)exact_band_kernel<N, S, 256, 4>;
-        case 1512: return (const void *)exact_band_kernel<N, S, 512, 2>;
+        // K2c: 100000 * (links requested a step ahead) + 10000 * rows per thread + threads
+        case 10064: return (const void *)exact_band_kernel<N, S, 64, 1, 8, false>;   // 64-thread shapes: the tests' way to
+        case 20064: return (const void *)exact_band_kernel<N, S, 64, 2, 4, false>;   // many bands and slots on small grids
+        case 30064: return (const void *)exact_band_kernel<N, S, 64, 3, 4, false>;
+        case 110064: return (const void *)exact_band_kernel<N, S, 64, 1, 4, true>;
+        case 120064: return (const void *)exact_band_kernel<N, S, 64, 2, 4, true>;
+        case 20256: return (const void *)exact_band_kernel<N, S, 256, 2, 2, false>;
+        case 40256: return (const void *)exact_band_kernel<N, S, 256, 4, 2, false>;
+        case 10512: return (const void *)exact_band_kernel<N, S, 512, 1, 2, false>;
+        case 110512: return (const void *)exact_band_kernel<N, S, 512, 1, 1, true>;
         case -1024: return (const void *)exact_ring_kernel<N, S, 1024, 1, N ? 1 : 4>;
         case -512: return (const void *)exact_ring_kernel<N, S, 512, 2, N ? 1 : 4>;
         case -256: return (const void *)exact_ring_kernel<N, S, 256, 2, 4>;
@@ -916,6 +1035,7 @@ static int ring_dispatch(bool noise, bool src, const K2Params &p, const RingCfg 
     const void *fn = ring_fn(noise, src, cfg.npt);
     int kb = cfg.kb, bands = cfg.bands;
     if (cfg.band_nt > 0) {
+        if (getenv("APDE_BAND_NOSYNC")) kb = -kb;
         void *args[] = {(void *)&p, (void *)&bands, (void *)&slots, (void *)&kb};
         APDE_CUDA(cudaLaunchCooperativeKernel(fn, dim3(slots * bands), dim3(cfg.block), args, 0, st));
         return APDE_OK;
@@ -954,17 +1074,26 @@ static int ring_configure(bool noise, bool src, int64_t rows, int64_t cols, int6
     bool want3 = false;
     if (force) want3 = !strcmp(force, "band");
     if (can3 && want3) {
-        int nt = rows - 2 >= 384 ? 512 : 256;
-        if (const char *v = getenv("APDE_BAND_NT")) {
-            const int b = atoi(v);
-            nt = b >= 512 ? 512 : (b >= 256 ? 256 : 64);
+        // launch shapes the kernel is instantiated for: (threads, rows per thread, links requested a step ahead)
+        static const int shapes[][3] = {{64, 1, 0}, {64, 2, 0}, {64, 3, 0}, {64, 1, 1}, {64, 2, 1},
+                                        {256, 2, 0}, {256, 4, 0}, {512, 1, 0}, {512, 1, 1}};
+        int nt = 512, r = 1, lpf = 0;  // the fastest measured shape (all shapes land within 15 %)
+        if (const char *v = getenv("APDE_BAND_NT")) nt = atoi(v);
+        if (const char *v = getenv("APDE_BAND_R")) r = atoi(v);
+        if (const char *v = getenv("APDE_BAND_LPF")) lpf = atoi(v) != 0;
+        bool known = false;
+        for (const auto &sh : shapes) known = known || (sh[0] == nt && sh[1] == r && sh[2] == lpf);
+        if (!known) {
+            set_error("exact band kernel: no instantiation for APDE_BAND_NT=%d APDE_BAND_R=%d APDE_BAND_LPF=%d", nt, r, lpf);
+            return APDE_EINVAL;
         }
         cfg->band_nt = nt;
+        cfg->band_r = r;
         cfg->block = nt;
-        cfg->npt = 1000 + nt;
+        cfg->npt = 100000 * lpf + 10000 * r + nt;
         cfg->kb = band_kb;
         cfg->smem = 0;
-        cfg->bands = (int)((rows - 2 + nt - 1) / nt);
+        cfg->bands = (int)((rows - 2 + nt * r - 1) / (nt * r));
     } else if (can2 && want2) {
         int block = 1024;
         while (block > 128 && block / 2 >= maxdiag) block /= 2;
@@ -997,8 +1126,8 @@ static int ring_configure(bool noise, bool src, int64_t rows, int64_t cols, int6
     if (cfg->band_nt > 0) {
         cfg->slots_max = (int)std::min<int64_t>(cfg->grid_max / cfg->bands, cols / (3 * cfg->kb + 4));
         if (cfg->slots_max < 1) {
-            set_error("exact band kernel: %d bands of %d rows exceed the %d co-resident CTAs", cfg->bands, cfg->band_nt,
-                      cfg->grid_max);
+            set_error("exact band kernel: %d bands of %d rows exceed the %d co-resident CTAs", cfg->bands,
+                      cfg->band_nt * cfg->band_r, cfg->grid_max);
             return APDE_EINVAL;
         }
     }

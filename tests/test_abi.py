@@ -178,7 +178,7 @@ def test_band_kernel_flag_protocol_never_deadlocks():
     import band_protocol_sim as sim
     rng = random.Random(7)
     for _ in range(60):
-        nt, kb = rng.choice([64, 256, 512]), rng.choice([1, 2, 4, 8, 16])
+        nt, kb = rng.choice([64, 128, 192, 256, 512, 1024]), rng.choice([1, 2, 4, 8, 16])  # nt = band height
         rows, cols, k = rng.randint(3, 1200), rng.randint(3 * kb + 4, 400), rng.randint(1, 80)
         assert sim.replay(rows, cols, nt, kb, k) == [], (rows, cols, nt, kb, k)
     for shape in ((67, 300, 64, 8, 90), (200, 130, 64, 4, 150), (131, 90, 64, 1, 77), (1100, 520, 512, 4, 45)):

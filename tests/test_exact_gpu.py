@@ -16,8 +16,12 @@ def _force_ring_kernel(path, monkeypatch):
     if not path.startswith("ring-"):
         return path
     kern = path[5:]
-    if kern.startswith("band"):
-        monkeypatch.setenv("APDE_BAND_NT", kern[4:])  # 64-row bands: several bands and sweep slots on small grids
+    if kern.startswith("band"):  # band<threads>[x<rows per thread>]; 64 threads: several bands and slots on small grids
+        lpf = kern.endswith("p")  # ...p: links requested one step ahead into registers
+        nt, _, r = kern[4:].rstrip("p").partition("x")
+        monkeypatch.setenv("APDE_BAND_NT", nt)
+        monkeypatch.setenv("APDE_BAND_R", r or "1")
+        monkeypatch.setenv("APDE_BAND_LPF", "1" if lpf else "0")
         kern = "band"
     monkeypatch.setenv("APDE_RING_KERNEL", kern)
     return "ring"
@@ -77,7 +81,9 @@ def test_python_classes_reproduce_reference(golden, name):
     (33, 65, 0.01, True, 40), (65, 33, 0.0, True, 40), (70, 70, 0.03, False, 31),
     (257, 129, 0.01, True, 11), (300, 300, 0.0, False, 13), (513, 700, 0.01, True, 6),
 ])
-@pytest.mark.parametrize("path", ["auto", "ring", "ring-k2", "ring-k2b", "ring-band64", "ring-band256", "ring-band512"])
+@pytest.mark.parametrize("path", ["auto", "ring", "ring-k2", "ring-k2b", "ring-band64", "ring-band64x2", "ring-band64x3",
+                                  "ring-band256x2", "ring-band256x4", "ring-band512", "ring-band64p", "ring-band64x2p",
+                                  "ring-band512p"])
 def test_fixed_sweeps_vs_oracle(rows, cols, sigma, src, k, path, monkeypatch):
     path = _force_ring_kernel(path, monkeypatch)  # every ring kernel on every shape (default picks one per problem)
     g0, nh, nv, s = random_problem(rows, cols, sigma, seed=rows * 1000 + cols, with_source=src)
@@ -89,7 +95,7 @@ def test_fixed_sweeps_vs_oracle(rows, cols, sigma, src, k, path, monkeypatch):
     assert g.tobytes() == ru.tobytes()
 
 
-@pytest.mark.parametrize("path", ["small", "ring", "ring-k2", "ring-k2b", "ring-band64"])
+@pytest.mark.parametrize("path", ["small", "ring", "ring-k2", "ring-k2b", "ring-band64", "ring-band64x3", "ring-band64x2p"])
 @pytest.mark.parametrize("tol", [1e-3, 1e-5, 3e-7])
 def test_early_stop_at_first_crossing(path, tol, monkeypatch):
     path = _force_ring_kernel(path, monkeypatch)
@@ -102,19 +108,27 @@ def test_early_stop_at_first_crossing(path, tol, monkeypatch):
     assert n == rn and hist.tobytes() == rh.tobytes() and g.tobytes() == ru.tobytes()
 
 
-@pytest.mark.parametrize("rows,cols,nt,kb,k", [
-    (200, 130, 64, 4, 150),    # 4 bands, 10 sweep slots: 15 rounds through the ring of slots
-    (131, 90, 64, 1, 77),      # progress exchanged every step; last band 1 row short of full
-    (67, 300, 64, 8, 90),      # 2 bands, the second with a single row (its thread is first AND last row)
-    (600, 257, 256, 4, 61),    # 3 bands of 256
-    (1100, 520, 512, 4, 45),   # 3 bands of 512, two CTAs per SM
+@pytest.mark.parametrize("rows,cols,nt,r,kb,k", [
+    (200, 130, 64, 1, 4, 150),    # 4 bands, 8 sweep slots: 19 rounds through the ring of slots
+    (131, 90, 64, 1, 1, 77),      # progress exchanged every step; last band 1 row short of full
+    (67, 300, 64, 1, 8, 90),      # 2 bands, the second with a single row (its thread is first AND last row)
+    (600, 257, 256, 2, 4, 61),    # 256 threads x 2 rows: 2 bands, the second 86 rows high
+    (1100, 520, 512, 1, 4, 45),   # 3 bands of 512, two CTAs per SM
+    (300, 140, 64, 2, 4, 120),    # two rows per thread: 3 bands of 128 rows, the last 42 rows high (second walker idle)
+    (260, 200, 64, 3, 2, 100),    # three rows per thread: 2 bands of 192 rows, the last row is walker 1's thread 1
+    (1500, 300, 256, 4, 4, 40),   # the benchmark shape: 256 threads x 4 rows, 2 bands, the second 474 rows high
+    (1030, 260, 256, 4, 4, 50),   # 256 threads x 4 rows: 2 bands, the last with 4 rows
 ])
-@pytest.mark.parametrize("sigma,src", [(0.01, True), (0.0, False)])
-def test_band_kernel_ring_of_slots_wraps(rows, cols, nt, kb, k, sigma, src, monkeypatch):
+@pytest.mark.parametrize("sigma,src,lpf", [(0.01, True, 0), (0.0, False, 0), (0.01, True, 1)])
+def test_band_kernel_ring_of_slots_wraps(rows, cols, nt, r, kb, k, sigma, src, lpf, monkeypatch):
     """K2c with more sweeps than sweep slots: every CTA runs several tasks back to back, threads of one CTA are on
     different sweeps at the same time, and slot 0 follows slot Gs-1 of the previous round."""
     monkeypatch.setenv("APDE_RING_KERNEL", "band")
     monkeypatch.setenv("APDE_BAND_NT", str(nt))
+    if lpf and (nt, r) not in ((64, 1), (64, 2), (512, 1)):
+        pytest.skip("shape not instantiated with links requested a step ahead")
+    monkeypatch.setenv("APDE_BAND_R", str(r))
+    monkeypatch.setenv("APDE_BAND_LPF", str(lpf))
     monkeypatch.setenv("APDE_BAND_KB", str(kb))
     g0, nh, nv, s = random_problem(rows, cols, sigma, seed=rows + cols, with_source=src)
     ru, rh, rn = oracle.gauss_seidel_mt(g0, nh, nv, s, k)

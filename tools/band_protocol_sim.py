@@ -10,7 +10,7 @@ import sys
 
 
 def launch_shape(rows, cols, nt, kb, k_sweeps, grid_max):
-    """(bands, slots) as ring_configure / solve_ring choose them."""
+    """(bands, slots) as ring_configure / solve_ring choose them; nt = band height (threads x rows per thread)."""
     bands = (rows - 2 + nt - 1) // nt
     slots_max = min(grid_max // bands, cols // (3 * kb + 4))
     if slots_max < 1:
