@@ -384,6 +384,8 @@ __device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned l
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+__device__ __forceinline__ void prefetch_l2_sector(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 struct K2Params {
     double *U;
     const double2 *LH, *LV;
@@ -392,7 +394,35 @@ struct K2Params {
     unsigned long long *progress;   // one counter per CTA (stride 16 to keep them on separate lines)
     int rows, cols, P;
     long long n_sweeps;             // sweeps in this launch
+    int flag_tid;                   // K2 / K2d: the thread that polls and publishes the progress counters
+    int l2_ahead;                   // K2 / K2d: diagonals the round's first CTA prefetches ahead into L2 (0: off)
+    int dbg;                        // TIMING EXPERIMENTS ONLY (wrong results): 1 no result store, 2 no release, 4 no block barrier
 };
+
+
+// The CTA of a round's first sweep (c == 0) is the first to touch a diagonal's links / source / values since the previous
+// round went by (4096^2: 0.67 GB per pass, the L2 holds 126 MB), so each of its node iterations waits for HBM instead of
+// L2 -- and every other sweep in flight follows it flag by flag at its pace (round 2, session 3: a sweep running ALONE
+// takes the same 26 ms as 148 in flight; the followers' flag threads spin ~37 polls per diagonal).  It therefore pulls the
+// operand rows of diagonal d + ahead into L2 at the start of step d: one prefetch per 32-byte sector, a handful per
+// thread and step, in a loop of its own so that the node loop's registers are untouched.
+template <bool HAS_NOISE, bool HAS_SRC>
+__device__ __forceinline__ void k2_leader_prefetch(const K2Params &p, int d, int tid, int nthr) {
+    const int da = d + p.l2_ahead;
+    const int dmax = p.rows + p.cols - 4;
+    if (da > dmax) return;
+    const int ilo = max(1, da - (p.cols - 2)), ihi = min(p.rows - 2, da - 1);
+    const long long oa = (long long)da * p.P;
+    if (HAS_NOISE)
+        for (int i = (ilo & ~1) + 2 * tid; i <= ihi; i += 2 * nthr) {  // 16-byte links: two per sector
+            prefetch_l2_sector(p.LV + oa + i);
+            prefetch_l2_sector(p.LH + oa + i);
+        }
+    for (int i = (ilo & ~3) + 4 * tid; i <= ihi + 1; i += 4 * nthr) {  // 8-byte values: four per sector
+        prefetch_l2_sector(p.U + oa + p.P + i);                         // south / east operands live on diagonal da + 1
+        if (HAS_SRC) prefetch_l2_sector(p.S + oa + i);
+    }
+}
 
 // MAXT is THE block size (the launch must use exactly MAXT threads: the node stride of a thread is a compile-time
 // constant so that a thread's further nodes are reached with immediate offsets); MINB shapes the register budget:
@@ -425,7 +455,8 @@ __global__ void __launch_bounds__(MAXT, MINB) exact_ring_kernel(K2Params p) {
             while (ld_acquire_u64(flag) < need) {
             }
         };
-        if (t > 0 && tid == 0) wait_pred(2);
+        const bool flagger = tid == p.flag_tid;
+        if (t > 0 && flagger) wait_pred(2);
         __syncthreads();
         // Element offset of this thread's first node of diagonal d, (d*P + ilo + tid), advanced incrementally: the
         // seven operand rows of a node (u on diagonals d-1, d, d+1; links and source on d-1 and d) then sit at fixed
@@ -433,6 +464,7 @@ __global__ void __launch_bounds__(MAXT, MINB) exact_ring_kernel(K2Params p) {
         // (which, at 64 registers, used to be recomputed and spilled for every node).
         long long off = 2 * P + max(1, 2 - (cols - 2)) + tid;
         for (int d = 2; d <= dmax; ++d) {
+            if (c == 0 && p.l2_ahead > 0) k2_leader_prefetch<HAS_NOISE, HAS_SRC>(p, d, tid, nthr);
             const int ilo = max(1, d - (cols - 2)), ihi = min(rows - 2, d - 1);
             const double *me0 = U + off;            // (d, i)
             const double *up0 = me0 - P;            // (d-1, i): west; [-1]: north
@@ -474,15 +506,15 @@ __global__ void __launch_bounds__(MAXT, MINB) exact_ring_kernel(K2Params p) {
                     if (ib + k <= ihi) {
                         const double nw = relax_node<HAS_NOISE, HAS_SRC>(un[e], us[e], uw[e], ue[e], ln[e], ls[e], lw[e], le[e], sv[e]);
                         mx = max_ignore_nan(mx, fabs(__dsub_rn(nw, old[e])));
-                        __stcg(me + k, nw);
+                        if (!(p.dbg & 1)) __stcg(me + k, nw);
                     }
                 }
             }
             // next diagonal: one pitch further, and one node further once the diagonal starts at the east column
             off += P + (max(1, d + 1 - (cols - 2)) - ilo);
-            if (t > 0 && tid == 0 && d < dmax) wait_pred(d + 1);
-            __syncthreads();
-            if (tid == 0)
+            if (t > 0 && flagger && d < dmax) wait_pred(d + 1);
+            if (!(p.dbg & 4)) __syncthreads();
+            if (flagger && !(p.dbg & 2))
                 st_release_u64(p.progress + (size_t)c * 16, (unsigned long long)(m * ND + (d - 1)));
         }
         // block max of this sweep -> residual_history[t]   (solver.py:281)
@@ -615,6 +647,138 @@ __global__ void __launch_bounds__(1024, 1) exact_ring2_kernel(K2Params p, int kb
         __syncthreads();
         if (tid < 32) {
             double v = (tid < (nthr + 31) / 32) ? red[tid] : 0.0;
+            v = warp_max(v);
+            if (tid == 0) p.hist[t] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2d: the K2 ring with the sweep's own operands resident in shared memory (mismatched meshes).
+//
+// K2 moves 112 B per update through L2 (5 u loads, four 16-byte {b, 1/b} links, 1 store) and at 4096^2 sits at
+// ~10 TB/s of L2 traffic with and without links, close to what the L2 delivers -- the hypothesis this kernel was built
+// to test.  Of those operands only south / east
+// (values of sweep t-1) and the node's own south / east links are new to the CTA; everything else it has touched one
+// diagonal earlier.  Two kinds of in-place shared-memory arrays carry them from diagonal to diagonal:
+//   row-indexed    Ui[i]  = u_t(i, j-1)        west value     written by node (i, j-1) as its result
+//                  Oi[i]  = u_{t-1}(i, j)      old value      written by node (i, j-1): its east operand
+//                  LHi[i] = nh[i, j-1]         west link      written by node (i, j-1): its east link
+//   column-indexed Uj[j]  = u_t(i-1, j)        north value    written by node (i-1, j) as its result
+//                  LVj[j] = nv[i-1, j]         north link     written by node (i-1, j): its south link
+// A diagonal holds at most one node per row and per column, so every cell is read and then rewritten by exactly one
+// thread per diagonal and the barrier K2 already has between diagonals orders the hand-over: no double buffering.
+// Per update: 16 B of u + 32 B of links loaded, 8 B stored (56 B through L2 instead of 112).  32 B per row + 24 B per
+// column of shared memory: 4096^2 needs 224 KB, so one 1024-thread CTA per SM.  The row's / column's first cells come
+// from the fixed ring (boundary values, links of row 0 / column 0), loaded at the start of every sweep; the old value of
+// a row's first interior node is the one operand nobody loaded before (one extra 8-byte load per diagonal).
+// NB = nodes whose L2 operands a thread requests before it relaxes any of them (as in K2; only 1 is instantiated:
+// 2 spills at the 64 registers a 1024-thread CTA leaves).
+// MEASURED (B200, 4096^2, 1 % mismatch, profiles/r2s3_exact_experiments.txt): bit-exact, 90 GLUP/s at K=1000 against
+// K2's 94-97, 65 against 64 at K=100 -- half the L2 bytes buy nothing, so L2 traffic is not what bounds the ring.  Opt-in
+// (APDE_RING_KERNEL=k2d), kept as the tested cross-check of that statement.
+// ------------------------------------------------------------------------------------------
+#ifndef K2D_DEFAULT
+#define K2D_DEFAULT false
+#endif
+static inline size_t k2d_smem_bytes(int64_t rows, int64_t cols) { return (size_t)(32 * rows + 24 * cols); }
+
+template <bool HAS_SRC, int NB>
+__global__ void __launch_bounds__(1024, 1) exact_ring_smem_kernel(K2Params p) {
+    extern __shared__ __align__(16) unsigned char k2d_smem[];
+    const int rows = p.rows, cols = p.cols;
+    const long long P = p.P;
+    constexpr int nthr = 1024;
+    double2 *LHi = reinterpret_cast<double2 *>(k2d_smem);  // rows
+    double2 *LVj = LHi + rows;                              // cols
+    double *Ui = reinterpret_cast<double *>(LVj + cols);    // rows
+    double *Oi = Ui + rows;                                 // rows
+    double *Uj = Oi + rows;                                 // cols
+    const int G = gridDim.x, c = blockIdx.x, tid = threadIdx.x;
+    const int dmax = rows + cols - 4;
+    const long long ND = dmax - 1;  // diagonals 2..dmax
+    const int pred = (c + G - 1) % G;
+    const bool flagger = tid == p.flag_tid;
+    __shared__ double red[32];
+    double *__restrict__ U = p.U;
+
+    long long m = 0;
+    for (long long t = c; t < p.n_sweeps; t += G, ++m) {
+        const long long mpred = (c == 0) ? m - 1 : m;
+        double mx = 0.0;
+        auto wait_pred = [&](int d) {  // as K2: sweep t-1 past diagonal d+1 before this sweep touches diagonal d
+            const unsigned long long need = (unsigned long long)(mpred * ND + (long long)(min(d + 1, dmax) - 1));
+            const unsigned long long *flag = p.progress + (size_t)pred * 16;
+            while (ld_acquire_u64(flag) < need) {
+            }
+        };
+        // the fixed ring: west value / west link of every row's first node, north value / north link of every column's
+        for (int i = tid; i < rows; i += nthr) {
+            Ui[i] = __ldcg(U + (long long)i * P + i);    // u(i, 0)
+            LHi[i] = __ldg(p.LH + (long long)i * P + i);  // nh[i, 0]
+        }
+        for (int j = tid; j < cols; j += nthr) {
+            Uj[j] = __ldcg(U + (long long)j * P);         // u(0, j)
+            LVj[j] = __ldg(p.LV + (long long)j * P);      // nv[0, j]
+        }
+        if (t > 0 && flagger) wait_pred(2);
+        __syncthreads();
+        long long off = 2 * P + max(1, 2 - (cols - 2)) + tid;  // (d*P + ilo + tid), advanced incrementally as in K2
+        for (int d = 2; d <= dmax; ++d) {
+            if (c == 0 && p.l2_ahead > 0) k2_leader_prefetch<true, HAS_SRC>(p, d, tid, nthr);
+            const int ilo = max(1, d - (cols - 2)), ihi = min(rows - 2, d - 1);
+            double *me0 = U + off;                               // (d, i); +P: east, +P+1: south
+            const double2 *lv0 = p.LV + off, *lh0 = p.LH + off;  // south / east link of the node
+            const double *s0 = p.S + off;
+            for (int ib = ilo + tid; ib <= ihi; ib += NB * nthr) {
+                const long long cb = ib - (ilo + tid);
+                double *me = me0 + cb;
+                const double2 *lv = lv0 + cb, *lh = lh0 + cb;
+                const double *sp = s0 + cb;
+                // the operands that come through L2, for all NB nodes before any is relaxed (their round trips overlap)
+                double us[NB], ue[NB], sv[NB], og[NB];
+                double2 ls[NB], le[NB];
+#pragma unroll
+                for (int e = 0; e < NB; ++e) {
+                    const int k = e * nthr;
+                    sv[e] = og[e] = 0.0;
+                    if (ib + k <= ihi) {
+                        us[e] = __ldcg(me + k + P + 1);
+                        ue[e] = __ldcg(me + k + P);
+                        ls[e] = __ldg(lv + k);
+                        le[e] = __ldg(lh + k);
+                        if (HAS_SRC) sv[e] = __ldg(sp + k);
+                        if (d - (ib + k) == 1) og[e] = __ldcg(me + k);  // the row's first interior node
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < NB; ++e) {
+                    const int k = e * nthr;
+                    const int i = ib + k, j = d - i;
+                    if (i <= ihi) {
+                        const double old = (j == 1) ? og[e] : Oi[i];
+                        const double nw = relax_node<true, HAS_SRC>(Uj[j], us[e], Ui[i], ue[e], LVj[j], ls[e], LHi[i], le[e], sv[e]);
+                        mx = max_ignore_nan(mx, fabs(__dsub_rn(nw, old)));
+                        if (!(p.dbg & 1)) __stcg(me + k, nw);
+                        Ui[i] = nw;
+                        Uj[j] = nw;
+                        Oi[i] = ue[e];
+                        LHi[i] = le[e];
+                        LVj[j] = ls[e];
+                    }
+                }
+            }
+            off += P + (max(1, d + 1 - (cols - 2)) - ilo);
+            if (t > 0 && flagger && d < dmax) wait_pred(d + 1);
+            if (!(p.dbg & 4)) __syncthreads();
+            if (flagger && !(p.dbg & 2)) st_release_u64(p.progress + (size_t)c * 16, (unsigned long long)(m * ND + (d - 1)));
+        }
+        mx = warp_max(mx);
+        if ((tid & 31) == 0) red[tid >> 5] = mx;
+        __syncthreads();
+        if (tid < 32) {
+            double v = red[tid];
             v = warp_max(v);
             if (tid == 0) p.hist[t] = v;
         }
@@ -1014,6 +1178,9 @@ static const void *ring_fn(int npt) {
         case 40256: return (const void *)exact_band_kernel<N, S, 256, 4, 2, false>;
         case 10512: return (const void *)exact_band_kernel<N, S, 512, 1, 2, false>;
         case 110512: return (const void *)exact_band_kernel<N, S, 512, 1, 1, true>;
+        case -2048:  // K2d (mismatched meshes only; ring_configure never asks for it otherwise)
+            if constexpr (N) return (const void *)exact_ring_smem_kernel<S, 1>;
+            else return (const void *)exact_ring_kernel<N, S, 1024, 1, 4>;
         case -1024: return (const void *)exact_ring_kernel<N, S, 1024, 1, N ? 1 : 4>;
         case -512: return (const void *)exact_ring_kernel<N, S, 512, 2, N ? 1 : 4>;
         case -256: return (const void *)exact_ring_kernel<N, S, 256, 2, 4>;
@@ -1063,6 +1230,12 @@ static int ring_configure(bool noise, bool src, int64_t rows, int64_t cols, int6
     bool want2 = !noise && !many;
     if (force && !strcmp(force, "k2")) want2 = false;
     if (force && !strcmp(force, "k2b")) want2 = true;
+    // K2d (operands of the sweep's own previous diagonal in shared memory): mismatched meshes whose 32 B per row +
+    // 24 B per column fit one CTA's shared memory (4096^2: 224 KB)
+    const size_t smem4 = k2d_smem_bytes(rows, cols);
+    const bool can4 = noise && smem4 + 1024 <= (size_t)prop.sharedMemPerBlockOptin;
+    bool want4 = K2D_DEFAULT;
+    if (force) want4 = !strcmp(force, "k2d");
     // K2c (row bands): the default wherever its ring of sweep slots can be made short enough for the width
     // (slots * (3*kb + 4) <= cols, see the kernel) -- i.e. everything but very narrow grids
     int band_kb = 4;
@@ -1094,6 +1267,10 @@ static int ring_configure(bool noise, bool src, int64_t rows, int64_t cols, int6
         cfg->kb = band_kb;
         cfg->smem = 0;
         cfg->bands = (int)((rows - 2 + nt * r - 1) / (nt * r));
+    } else if (can4 && want4) {
+        cfg->block = 1024;
+        cfg->npt = -2048;
+        cfg->smem = smem4;
     } else if (can2 && want2) {
         int block = 1024;
         while (block > 128 && block / 2 >= maxdiag) block /= 2;
@@ -1197,6 +1374,15 @@ static int solve_ring(double *grid, const double *nh, const double *nv, const do
     p.rows = (int)rows;
     p.cols = (int)cols;
     p.P = P;
+    // The flag exchange (acquire-poll of the predecessor, release of the own counter) is the LAST thread's job: it has
+    // one node less than thread 0 on all but 1 in 32 diagonals, so the release fence sits in that slack instead of on
+    // the block's critical path.  APDE_RING_FLAGTID=0 restores thread 0 (measurement aid).
+    p.flag_tid = cfg.block - 1;
+    if (const char *v = getenv("APDE_RING_FLAGTID")) p.flag_tid = std::min(cfg.block - 1, std::max(0, atoi(v)));
+    p.dbg = 0;
+    if (const char *v = getenv("APDE_RING_DEBUG")) p.dbg = atoi(v);  // timing experiments only: results are wrong
+    p.l2_ahead = 4;
+    if (const char *v = getenv("APDE_RING_L2AHEAD")) p.l2_ahead = std::min(64, std::max(0, atoi(v)));
 
     std::vector<double> hbuf;
     int64_t done = 0, result_iters = max_iter;

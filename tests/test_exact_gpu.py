@@ -43,7 +43,7 @@ def test_golden_bit_exact_auto_path(golden, name):
     assert g.tobytes() == c["solution"].tobytes()
 
 
-@pytest.mark.parametrize("kern", ["default", "ring-k2", "ring-band64"])
+@pytest.mark.parametrize("kern", ["default", "ring-k2", "ring-k2d", "ring-band64"])
 @pytest.mark.parametrize("name", [n for n in GOLDEN_NAMES if n not in ("rows2", "cols1")])
 def test_golden_bit_exact_ring_path(golden, name, kern, monkeypatch):
     """Force the multi-CTA kernels on every case, including the ones that fit one CTA;
@@ -81,7 +81,7 @@ def test_python_classes_reproduce_reference(golden, name):
     (33, 65, 0.01, True, 40), (65, 33, 0.0, True, 40), (70, 70, 0.03, False, 31),
     (257, 129, 0.01, True, 11), (300, 300, 0.0, False, 13), (513, 700, 0.01, True, 6),
 ])
-@pytest.mark.parametrize("path", ["auto", "ring", "ring-k2", "ring-k2b", "ring-band64", "ring-band64x2", "ring-band64x3",
+@pytest.mark.parametrize("path", ["auto", "ring", "ring-k2", "ring-k2b", "ring-k2d", "ring-band64", "ring-band64x2", "ring-band64x3",
                                   "ring-band256x2", "ring-band256x4", "ring-band512", "ring-band64p", "ring-band64x2p",
                                   "ring-band512p"])
 def test_fixed_sweeps_vs_oracle(rows, cols, sigma, src, k, path, monkeypatch):
@@ -95,7 +95,7 @@ def test_fixed_sweeps_vs_oracle(rows, cols, sigma, src, k, path, monkeypatch):
     assert g.tobytes() == ru.tobytes()
 
 
-@pytest.mark.parametrize("path", ["small", "ring", "ring-k2", "ring-k2b", "ring-band64", "ring-band64x3", "ring-band64x2p"])
+@pytest.mark.parametrize("path", ["small", "ring", "ring-k2", "ring-k2b", "ring-k2d", "ring-band64", "ring-band64x3", "ring-band64x2p"])
 @pytest.mark.parametrize("tol", [1e-3, 1e-5, 3e-7])
 def test_early_stop_at_first_crossing(path, tol, monkeypatch):
     path = _force_ring_kernel(path, monkeypatch)
@@ -247,7 +247,7 @@ def test_unsafe_links_take_the_general_division():
     g0[10, 10] = -0.0
     g0[11, 3] = 5e-324
     import os
-    for path, kern in (("small", None), ("ring", "k2"), ("ring", "band")):
+    for path, kern in (("small", None), ("ring", "k2"), ("ring", "k2d"), ("ring", "band")):
         if kern:
             os.environ["APDE_RING_KERNEL"] = kern
         try:
@@ -272,18 +272,22 @@ def test_config3_size_4096_mismatch_iterates():
     assert it == k and hist.tobytes() == rh.tobytes() and g.tobytes() == ru.tobytes()
 
 
-def test_config3_size_4096_many_sweeps_in_flight():
-    """Config 3 with more sweeps than the ring has CTA slots (2 x 148 = 296 on B200): K = 420 sweeps,
-    so the ring wraps (CTA c runs sweeps c, c+G, ...) with every slot busy.  Grid and all 420 residuals
-    equal the CPU oracle (column-block pipelined over the host threads, bitwise equal to the serial loop)."""
+def test_config3_size_4096_many_sweeps_in_flight(monkeypatch):
+    """Config 3 with more sweeps than the ring has CTA slots (148 for K2d, 2 x 148 = 296 for K2 on B200): K = 420
+    sweeps, so the ring wraps (CTA c runs sweeps c, c+G, ...) with every slot busy.  Grid and all 420 residuals
+    equal the CPU oracle (column-block pipelined over the host threads, bitwise equal to the serial loop) for the
+    default kernel choice and for both ring kernels forced."""
     n, k = 4096, 420
     s = AnalogPDESolver(rows=n, cols=n, noise_level=0.01, rng_seed=0)
     g0 = np.zeros((n, n))
     g0[0, :] = 1.0
     ru, rh, _ = oracle.gauss_seidel_mt(g0, s._noise_h, s._noise_v, None, k)
-    g = g0.copy()
-    hist, it, _ = _backend.solve("exact", g, s._noise_h, s._noise_v, None, 0.0, k)
-    assert it == k and hist.tobytes() == rh.tobytes() and g.tobytes() == ru.tobytes()
+    for kern in (None, "ring-k2", "ring-k2d"):
+        if kern:
+            _force_ring_kernel(kern, monkeypatch)
+        g = g0.copy()
+        hist, it, _ = _backend.solve("exact", g, s._noise_h, s._noise_v, None, 0.0, k)
+        assert it == k and hist.tobytes() == rh.tobytes() and g.tobytes() == ru.tobytes(), kern
 
 
 def test_poisson_demo_numbers():

@@ -12,6 +12,7 @@ ap.add_argument("--n", type=int, default=4096)
 ap.add_argument("--k", type=int, default=100)
 ap.add_argument("--noise", type=float, default=0.01)
 ap.add_argument("--no-check", action="store_true")
+ap.add_argument("--warmup-k", type=int, default=2)
 a = ap.parse_args()
 n, k = a.n, a.k
 rng = np.random.default_rng(0)
@@ -21,7 +22,7 @@ if a.noise > 0:
     nv = 1.0 + a.noise * rng.standard_normal((n - 1, n))
 g0 = np.zeros((n, n)); g0[0, :] = 1.0
 g = g0.copy()
-_backend.solve("exact", g0.copy(), nh, nv, None, 0.0, 2)  # warm-up (context, module load)
+_backend.solve("exact", g0.copy(), nh, nv, None, 0.0, a.warmup_k)  # warm-up (context, module load)
 t0 = time.perf_counter()
 hist, it, ksec = _backend.solve("exact", g, nh, nv, None, 0.0, k)
 wall = time.perf_counter() - t0
