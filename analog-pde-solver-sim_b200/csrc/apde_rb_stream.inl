@@ -52,10 +52,11 @@ struct StreamArgs {
     T *resid;  // slot of the first sweep of this pass
     const int *stop;  // optional device flag: set => the solve has converged, do nothing
     long long pitch, padl, lrows, cols, grows, row0;
-    long long own_lo, own_hi;
-    long long rbh;                 // row-block height
-    long long blk_a0, blk_an;      // row blocks [blk_a0, blk_a0+blk_an) ...
-    long long blk_b0, blk_bn;      // ... and [blk_b0, blk_b0+blk_bn)
+    // two groups of row blocks: blk_an blocks of rbh rows cut from the local rows [own_lo, own_hi), then blk_bn blocks of
+    // rbh_b rows cut from [lo_b, hi_b) -- a whole strip is one group; the strip-edge phase of a multi-GPU pass is one short
+    // block per side, the interior phase the rows in between
+    long long own_lo, own_hi, rbh, blk_an;
+    long long lo_b, hi_b, rbh_b, blk_bn;
     long long n_strips, n_items;
 };
 
@@ -383,10 +384,11 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
     for (long long item = warp_id; item < a.n_items; item += n_warps) {
         const long long bsel = item / a.n_strips;
         const long long sidx = item - bsel * a.n_strips;
-        const long long blk = bsel < a.blk_an ? a.blk_a0 + bsel : a.blk_b0 + (bsel - a.blk_an);
+        const bool grp_a = bsel < a.blk_an;
+        const long long blk = grp_a ? bsel : bsel - a.blk_an, bh = grp_a ? a.rbh : a.rbh_b;
         // local row indices fit 32 bits; only element offsets are 64-bit (carried in the pointers)
-        const int rb0 = (int)(a.own_lo + blk * a.rbh);
-        const int rb1 = (int)min((long long)rb0 + a.rbh, a.own_hi);
+        const int rb0 = (int)((grp_a ? a.own_lo : a.lo_b) + blk * bh);
+        const int rb1 = (int)min((long long)rb0 + bh, grp_a ? a.own_hi : a.hi_b);
         const long long jl0 = sidx * VW - HCA + (long long)C * lane;  // first column of this lane (even)
         const bool lane_valid = (C * lane >= HCA) && (C * lane < CW - HCA) && (jl0 < a.cols);
         unsigned colmask = 0;  // bit q: column jl0+q is an interior column
@@ -798,23 +800,38 @@ int launch_pass(apde_plan *p, StreamArgs &a, const BlockReq &rq, cudaStream_t st
     }
     const long long warps_per_block = RBS_THREADS / 32;
     const long long resident_warps = (long long)p->sm_count * blocks_per_sm * warps_per_block;
-    // ---- row blocks (the same partition in every phase of a pass) ------------------------------------------
-    a.rbh = rq.forced_rbh > 0 ? std::max(rq.forced_rbh, rq.halo)  // an edge block must hold the rows the halo exchange sends
-                              : pick_row_block(rq.owned, a.n_strips, resident_warps, 2 * TD, rq.halo);
-    const long long nblk = (rq.owned + a.rbh - 1) / a.rbh;
-    // edge blocks: the leading / trailing row blocks that together hold the `halo` outermost owned
-    // rows on a side with a neighbour strip (those rows are what the halo exchange ships right after
-    // phase 1).  Blocks are rbh >= halo rows, except the last one, which holds the remainder: when
-    // that is shorter than the halo the block before it is an edge block too.
-    const long long last_rows = rq.owned - (nblk - 1) * a.rbh;
-    long long ea = (rq.top_nb ? 1 : 0), eb = (rq.bot_nb ? (last_rows < rq.halo ? 2 : 1) : 0);
-    if (ea + eb > nblk) { ea = std::min<long long>(ea, nblk); eb = nblk - ea; }
-    if (rq.phase == 0) {
-        a.blk_a0 = 0; a.blk_an = nblk; a.blk_b0 = 0; a.blk_bn = 0;
-    } else if (rq.phase == 1) {
-        a.blk_a0 = 0; a.blk_an = ea; a.blk_b0 = nblk - eb; a.blk_bn = eb;
+    // ---- row blocks ---------------------------------------------------------------------------------------------
+    // Unphased: the owned rows in blocks of the modelled-best height.  Phased (multi-GPU pass): phase 1 relaxes ONE SHORT
+    // block per side that has a neighbour strip -- it holds the `halo` outermost owned rows the exchange ships -- and phase
+    // 2 the rows in between.  Round 2 cut edge blocks from the same partition as everything else (1024 rows at 16384^2), so
+    // the "edge" kernel ran as long as the whole pass and the halo exchange started when the interior was done
+    // (profiles/r2s3_step_timeline.txt: edge 1.62 ms of a 1.72 ms pass); 64-row edge blocks finish in a tenth of a pass
+    // and the exchange hides behind the interior.  Results do not depend on the partition (every row block is bitwise
+    // the same function of the input buffer).
+    const long long own_lo = a.own_lo, own_hi = a.own_hi;
+    const long long eh = rq.forced_rbh > 0 ? std::max(rq.forced_rbh, rq.halo) : std::max<long long>(rq.halo, 64);
+    long long et = rq.top_nb ? eh : 0, eb = rq.bot_nb ? eh : 0;
+    const bool split = rq.phase != 0 && et + eb > 0 && et + eb < rq.owned;  // else: phase 1 takes the whole strip
+    a.blk_an = a.blk_bn = 0;
+    a.lo_b = a.hi_b = own_hi;
+    a.rbh = a.rbh_b = 1;
+    if (rq.phase == 1 && split) {
+        a.own_hi = own_lo + et;
+        a.rbh = std::max<long long>(et, 1);
+        a.blk_an = et > 0 ? 1 : 0;
+        a.lo_b = own_hi - eb;
+        a.rbh_b = std::max<long long>(eb, 1);
+        a.blk_bn = eb > 0 ? 1 : 0;
+    } else if (rq.phase == 2 && !split) {
+        return APDE_OK;  // phase 1 did everything
     } else {
-        a.blk_a0 = ea; a.blk_an = nblk - ea - eb; a.blk_b0 = 0; a.blk_bn = 0;
+        if (rq.phase == 2) {
+            a.own_lo = own_lo + et;
+            a.own_hi = own_hi - eb;
+        }
+        const long long rows = a.own_hi - a.own_lo;
+        a.rbh = rq.forced_rbh > 0 ? std::max(rq.forced_rbh, rq.halo) : pick_row_block(rows, a.n_strips, resident_warps, 2 * TD, rq.halo);
+        a.blk_an = (rows + a.rbh - 1) / a.rbh;
     }
     a.n_items = (a.blk_an + a.blk_bn) * a.n_strips;
     if (a.n_items <= 0) return APDE_OK;

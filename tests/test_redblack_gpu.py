@@ -218,6 +218,50 @@ def test_three_strips_phased_overlap_protocol(dt, cuts, monkeypatch):
     assert hist.tobytes() == ref_hist.tobytes()
 
 
+@pytest.mark.parametrize("cuts", [[0, 200, 330, 600], [0, 130, 470, 600], [0, 64, 193, 600]])
+@pytest.mark.parametrize("dt,noise", [(np.float64, True), (np.float64, False), (np.float32, True)])
+def test_phased_passes_with_default_edge_blocks(dt, noise, cuts):
+    """The same protocol with the partition the launcher picks itself: one 64-row edge block per side with a neighbour
+    in phase 1, the rows in between in phase 2.  The cuts give an interior of 2 rows (130 = 64 + 2 + 64), an interior of
+    1 row (129), strips no taller than their edge blocks (64: phase 1 relaxes the whole strip, phase 2 launches
+    nothing) and end strips with one edge block only."""
+    rows, cols, depth = 600, 333, 4
+    groups = [4, 4, 3, 1]
+    g0, nh, nv, s = random_problem(rows, cols, 0.01 if noise else 0.0, seed=29)
+    lib = _backend.load()
+    kw = dict(dtype=dt, has_noise=noise, has_source=True, temporal_depth=depth)
+    with _backend.Plan(rows, cols, **kw) as whole:
+        whole.upload(g0, nh, nv, s)
+        whole.run(sum(groups), 0)
+        ref = whole.download()
+        ref_hist = whole.residuals(0, sum(groups))
+    plans = [_backend.Plan(rows, cols, cuts[k], cuts[k + 1], **kw) for k in range(3)]
+    for p in plans:
+        p.upload(g0, nh, nv, s)
+    base = 0
+    for n in groups:
+        for p in plans:
+            p.clear_residuals(base, n)
+            p.run(n, base, phase=1)
+        for k in range(2):
+            send_dn, recv_dn, nb = plans[k].halo(1)
+            send_up, recv_up, nb2 = plans[k + 1].halo(0)
+            assert nb == nb2
+            _backend.check(lib.apde_memcpy_dtod(recv_up, send_dn, nb, None))
+            _backend.check(lib.apde_memcpy_dtod(recv_dn, send_up, nb, None))
+        for p in plans:
+            p.run(n, base, phase=2)
+        base += n
+    out = np.zeros((rows, cols))
+    hist = np.zeros(sum(groups))
+    for p in plans:
+        p.download(out)
+        hist = np.maximum(hist, p.residuals(0, sum(groups)))
+        p.close()
+    assert out.tobytes() == ref.tobytes()
+    assert hist.tobytes() == ref_hist.tobytes()
+
+
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
 def test_device_energy_matches_energy_model(dt):
     """apde_plan_energy_sums (two strips) vs EnergyModel.analog_energy_joules on the downloaded grid."""
