@@ -84,6 +84,9 @@ inline Geo make_geo(const apde_plan *p) {
 // implemented in apde_rb_stream_f64.cu / apde_rb_stream_f32.cu
 int run_stream_f64(apde_plan *p, int64_t n_sweeps, int64_t sweep_base, int phase, cudaStream_t st);
 int run_stream_f32(apde_plan *p, int64_t n_sweeps, int64_t sweep_base, int phase, cudaStream_t st);
+// one pass over a band of local rows with explicit buffers (the streamed one-shot solve)
+int run_stream_band_f64(apde_plan *p, int td, int64_t resid_slot, int src_buf, int64_t row_lo, int64_t row_hi, int64_t rbh, cudaStream_t st);
+int run_stream_band_f32(apde_plan *p, int td, int64_t resid_slot, int src_buf, int64_t row_lo, int64_t row_hi, int64_t rbh, cudaStream_t st);
 // implemented in apde_rb_pipe_f64.cu / apde_rb_pipe_f32.cu
 int run_pipe_f64(apde_plan *p, int64_t n_sweeps, int64_t sweep_base, int phase, cudaStream_t st);
 int run_pipe_f32(apde_plan *p, int64_t n_sweeps, int64_t sweep_base, int phase, cudaStream_t st);

@@ -757,6 +757,7 @@ struct BlockReq {
     bool top_nb, bot_nb;
     int phase;
     long long forced_rbh;  // > 0: APDE_ROW_BLOCK
+    long long band_lo = 0, band_hi = 0, band_rbh = 0;  // band_hi > band_lo: relax exactly these local rows (streamed solve)
 };
 
 // Row-block height.  One launch runs n_blocks * n_strips work items on W resident warps in ceil(items / W) rounds of
@@ -815,7 +816,12 @@ int launch_pass(apde_plan *p, StreamArgs &a, const BlockReq &rq, cudaStream_t st
     a.blk_an = a.blk_bn = 0;
     a.lo_b = a.hi_b = own_hi;
     a.rbh = a.rbh_b = 1;
-    if (rq.phase == 1 && split) {
+    if (rq.band_hi > rq.band_lo) {
+        a.own_lo = rq.band_lo;
+        a.own_hi = rq.band_hi;
+        a.rbh = std::max<long long>(rq.band_rbh, 8);
+        a.blk_an = (rq.band_hi - rq.band_lo + a.rbh - 1) / a.rbh;
+    } else if (rq.phase == 1 && split) {
         a.own_hi = own_lo + et;
         a.rbh = std::max<long long>(et, 1);
         a.blk_an = et > 0 ? 1 : 0;
@@ -868,6 +874,33 @@ int launch_any(apde_plan *p, StreamArgs &a, const BlockReq &rq, int td, cudaStre
     return launch_depth<C, false, false>(p, a, rq, td, st);
 }
 
+// kernel arguments of one pass of td fused sweeps reading u[src_buf], writing u[dst_buf]; the row blocks are filled in
+// by launch_pass
+static StreamArgs make_stream_args(apde_plan *p, const Geo &g, int src_buf, int dst_buf, int64_t resid_slot, int td) {
+    StreamArgs a;
+    a.in = p->U<T>(src_buf);
+    a.out = p->U<T>(dst_buf);
+    const int lane_cols = p->lane_vectors == 2 ? RBS_C2 : RBS_C1;
+    const bool split = rbs_split((int)sizeof(T), lane_cols, p->d.has_noise);
+    a.src = split ? p->SC<T>() : p->S<T>();
+    a.gh = split ? p->GHC<T>() : p->GH<T>();
+    a.gv = split ? p->GVC<T>() : p->GV<T>();
+    a.resid = p->resid.as<T>() + resid_slot;
+    a.stop = p->stop_flag;
+    a.pitch = g.pitch;
+    a.padl = g.padl;
+    a.lrows = g.lrows;
+    a.cols = g.cols;
+    a.grows = g.grows;
+    a.row0 = g.row0;
+    a.own_lo = g.own_lo;
+    a.own_hi = g.own_hi;
+    const int HCA = ((2 * td + lane_cols - 1) / lane_cols) * lane_cols;
+    const int VW = 32 * lane_cols - 2 * HCA;
+    a.n_strips = (g.cols + VW - 1) / VW;
+    return a;
+}
+
 }  // namespace
 
 // Runs n_sweeps sweeps as passes of <= temporal_depth fused sweeps; ping-pongs u[cur] -> u[1-cur].
@@ -886,27 +919,7 @@ int RBS_FN(apde_plan *p, int64_t n_sweeps, int64_t sweep_base, int phase, cudaSt
         const int td = (int)std::min<int64_t>(max_td, n_sweeps - done);
         // a phase-2 call completes the pass a phase-1 call started: same buffers
         const int src_buf = p->cur, dst_buf = 1 - p->cur;
-        StreamArgs a;
-        a.in = p->U<T>(src_buf);
-        a.out = p->U<T>(dst_buf);
-        const int lane_cols = p->lane_vectors == 2 ? RBS_C2 : RBS_C1;
-        const bool split = rbs_split((int)sizeof(T), lane_cols, p->d.has_noise);
-        a.src = split ? p->SC<T>() : p->S<T>();
-        a.gh = split ? p->GHC<T>() : p->GH<T>();
-        a.gv = split ? p->GVC<T>() : p->GV<T>();
-        a.resid = p->resid.as<T>() + sweep_base + done;
-        a.stop = p->stop_flag;
-        a.pitch = g.pitch;
-        a.padl = g.padl;
-        a.lrows = g.lrows;
-        a.cols = g.cols;
-        a.grows = g.grows;
-        a.row0 = g.row0;
-        a.own_lo = g.own_lo;
-        a.own_hi = g.own_hi;
-        const int HCA = ((2 * td + lane_cols - 1) / lane_cols) * lane_cols;
-        const int VW = 32 * lane_cols - 2 * HCA;
-        a.n_strips = (g.cols + VW - 1) / VW;
+        StreamArgs a = make_stream_args(p, g, src_buf, dst_buf, sweep_base + done, td);
         BlockReq rq;
         rq.owned = g.own_hi - g.own_lo;
         rq.halo = p->halo;
@@ -928,6 +941,30 @@ int RBS_FN(apde_plan *p, int64_t n_sweeps, int64_t sweep_base, int phase, cudaSt
     }
     APDE_CUDA(cudaGetLastError());
     return APDE_OK;
+}
+
+
+// One pass of td <= 4 fused sweeps over the local rows [row_lo, row_hi) only, reading u[src_buf] and writing u[1 - src_buf],
+// in row blocks of `rbh` rows.  The caller (the streamed one-shot solve, apde_redblack.cu) owns the schedule: p->cur is
+// neither read nor changed.  Rows outside the band are untouched in both buffers.
+int RBS_BAND_FN(apde_plan *p, int td, int64_t resid_slot, int src_buf, int64_t row_lo, int64_t row_hi, int64_t rbh, cudaStream_t st) {
+    const Geo g = make_geo(p);
+    if (g.cols < 3 || g.lrows < 3 || td <= 0 || row_hi <= row_lo) return APDE_OK;
+    if (td > 4 || row_lo < g.own_lo || row_hi > g.own_hi) {
+        set_error("rb_stream band: bad pass (depth %d, rows [%lld, %lld))", td, (long long)row_lo, (long long)row_hi);
+        return APDE_EINVAL;
+    }
+    StreamArgs a = make_stream_args(p, g, src_buf, 1 - src_buf, resid_slot, td);
+    BlockReq rq;
+    rq.owned = g.own_hi - g.own_lo;
+    rq.halo = p->halo;
+    rq.top_nb = rq.bot_nb = false;
+    rq.phase = 0;
+    rq.forced_rbh = 0;
+    rq.band_lo = row_lo;
+    rq.band_hi = row_hi;
+    rq.band_rbh = rbh;
+    return p->lane_vectors == 2 ? launch_any<RBS_C2>(p, a, rq, td, st) : launch_any<RBS_C1>(p, a, rq, td, st);
 }
 
 #undef RBS_SLOT

@@ -820,6 +820,182 @@ void release_cached_plan() {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Streamed one-shot solve (fixed sweep count): upload, sweeps and download overlap.
+//
+// A one-shot call moves the whole problem over PCIe twice (16384^2 fp64 Poisson: 4.3 GB up, 2.1 GB down = 123 ms at
+// ~52 GB/s) around 107 ms of sweeps; run one after the other that is 230 ms.  Information travels only 2*TD rows per
+// fused pass, so the passes can follow the upload front and the download can follow the last pass -- provided the unit
+// that is scheduled does not widen the dependence cone.  Cutting every pass into the SAME row bands does (pass p of band
+// b needs pass p-1 of band b+1: 64 passes = 64 bands behind).  Here the bands of pass p are shifted UP by (p-1)*2*TD rows
+// (parallelogram tiling): pass p of band b = rows [b*B - s_p, (b+1)*B - s_p), s_p = (p-1)*h, h = 2*TD.  Then
+//   * it reads pass p-1 on rows [b*B - s_p - h, (b+1)*B - s_p + h) = up to the END of pass p-1's band b: every pass of
+//     band b can run as soon as band b-1 is finished and rows < (b+1)*B + h are on the device;
+//   * it writes buffer p%2 on rows whose pass p-2 values nobody needs any more (the next band's pass p-1 reads from
+//     (b+1)*B - s_{p-1} - h = (b+1)*B - s_p upwards) -- the two ping-pong buffers suffice;
+//   * after its last pass a band is final and goes back to the host while the next bands are still being relaxed.
+// Order on the device: band-major (all passes of band 0, then band 1, ...) on one compute stream; uploads (copy + pack +
+// colour split per chunk of B rows) run ahead on a second stream, downloads (unpack + copy per band) behind on a third.
+// Every node sees exactly the operands of the unstreamed schedule, so the result and the residual history are bitwise
+// the same (tests/test_redblack_gpu.py::test_streamed_solve_*).  Only for runs that cannot stop early (tol <= 0): a
+// convergence decision needs a sweep's residual over the WHOLE grid before later sweeps may count.
+// ------------------------------------------------------------------------------------------
+template <typename T, bool RECIP>
+__global__ void pack_rows_kernel(const double *__restrict__ in, long long nrows, long long in_cols, T *__restrict__ out0,
+                                 T *__restrict__ out1, long long pitch, long long padl) {
+    const long long n = nrows * in_cols;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        const long long r = k / in_cols, j = k - r * in_cols;
+        double v = in[k];
+        if (RECIP) v = 1.0 / v;
+        out0[r * pitch + padl + j] = (T)v;
+        if (out1) out1[r * pitch + padl + j] = (T)v;
+    }
+}
+
+struct StreamSet {
+    cudaStream_t up = nullptr, run = nullptr, down = nullptr;
+    std::vector<cudaEvent_t> ev;
+    ~StreamSet() {
+        for (auto e : ev)
+            if (e) cudaEventDestroy(e);
+        for (auto s : {up, run, down})
+            if (s) cudaStreamDestroy(s);
+    }
+    int event(cudaEvent_t *out) {
+        cudaEvent_t e = nullptr;
+        APDE_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ev.push_back(e);
+        *out = e;
+        return APDE_OK;
+    }
+};
+
+template <typename T>
+static int solve_streamed_t(apde_plan *p, double *grid, const double *nh, const double *nv, const double *src,
+                            int64_t n_sweeps, int64_t B, int64_t rbh, float *kernel_ms) {
+    const Geo g = make_geo(p);
+    const int64_t rows = p->d.grows, cols = p->d.cols, pitch = p->pitch;
+    const int TD = std::min(p->d.temporal_depth, 4);
+    const int64_t h = 2 * TD, P = (n_sweeps + TD - 1) / TD;
+    const int64_t skew_max = (P - 1) * h;
+    const int64_t nb = (rows + skew_max + B - 1) / B;  // bands: the last ones exist only for the late (far shifted) passes
+    const int64_t nchunk = (rows + B - 1) / B + 1;
+    auto chunk_edge = [&](int64_t c) { return c <= 0 ? (int64_t)0 : std::min<int64_t>(rows, c * B + h); };  // rows < (b+1)*B + h feed band b
+    auto band_edge = [&](int64_t b, int64_t pass /*1-based*/) { return std::min<int64_t>(rows, std::max<int64_t>(0, b * B - (pass - 1) * h)); };
+
+    // staging: one chunk going up, one band coming down
+    const size_t up_rows = (size_t)(B + h), stage_elems = (up_rows + (size_t)B) * (size_t)cols;
+    if (p->stage.bytes < stage_elems * 8) APDE_TRY(p->stage.alloc(stage_elems * 8));
+    double *stage_up = p->stage.as<double>(), *stage_dn = stage_up + up_rows * (size_t)cols;
+    // colour-split planes: allocated (and their padding rows zeroed) once per plan
+    const size_t plane_bytes = p->plane_elems() * sizeof(T);
+    auto ensure_plane = [&](DevBuf &from, DevBuf &to) -> int {
+        if (!from.p || to.p) return APDE_OK;
+        APDE_TRY(to.alloc(plane_bytes));
+        APDE_CUDA(cudaMemset(to.p, 0, plane_bytes));
+        return APDE_OK;
+    };
+    APDE_TRY(ensure_plane(p->src, p->src_cs));
+    APDE_TRY(ensure_plane(p->gh, p->gh_cs));
+    APDE_TRY(ensure_plane(p->gv, p->gv_cs));
+    APDE_TRY(plan_ensure_resid(p, n_sweeps));
+    APDE_CUDA(cudaDeviceSynchronize());  // the legacy stream may still hold work on these buffers
+
+    StreamSet ss;
+    APDE_CUDA(cudaStreamCreateWithFlags(&ss.up, cudaStreamNonBlocking));
+    APDE_CUDA(cudaStreamCreateWithFlags(&ss.run, cudaStreamNonBlocking));
+    APDE_CUDA(cudaStreamCreateWithFlags(&ss.down, cudaStreamNonBlocking));
+    const int tb = 256, tg = p->sm_count * 8;
+    APDE_CUDA(cudaMemsetAsync(p->resid.as<T>(), 0, (size_t)n_sweeps * sizeof(T), ss.run));
+
+    // ---- one loop queues chunk i (upload stream), band i (compute stream) and the download of band i-1 ------------
+    // (all asynchronous from pinned host memory; with pageable memory the copies block the host, and this order keeps
+    // the compute stream fed while they do)
+    std::vector<cudaEvent_t> up_done((size_t)nchunk, nullptr), band_done((size_t)nb, nullptr);
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    APDE_CUDA(cudaEventCreate(&t0));
+    APDE_CUDA(cudaEventCreate(&t1));
+    struct Timers {
+        cudaEvent_t a, b;
+        ~Timers() {
+            cudaEventDestroy(a);
+            cudaEventDestroy(b);
+        }
+    } timers{t0, t1};
+    const int final_buf = (int)(P % 2);
+    const T *final_u = p->U<T>(final_buf);
+    auto upload_chunk = [&](int64_t c) -> int {
+        const int64_t r0 = chunk_edge(c), r1 = chunk_edge(c + 1);
+        if (r1 > r0) {
+            const int64_t n = r1 - r0;
+            auto one = [&](const double *host, int64_t in_cols, int64_t n_rows, bool recip, T *dst0, T *dst1, T *plane, T *plane_cs) -> int {
+                if (n_rows <= 0 || in_cols <= 0) return APDE_OK;
+                APDE_CUDA(cudaMemcpyAsync(stage_up, host + (size_t)r0 * (size_t)in_cols, (size_t)n_rows * (size_t)in_cols * 8,
+                                          cudaMemcpyHostToDevice, ss.up));
+                if (recip) pack_rows_kernel<T, true><<<tg, tb, 0, ss.up>>>(stage_up, n_rows, in_cols, dst0 + r0 * pitch, dst1 ? dst1 + r0 * pitch : nullptr, pitch, p->padl);
+                else pack_rows_kernel<T, false><<<tg, tb, 0, ss.up>>>(stage_up, n_rows, in_cols, dst0 + r0 * pitch, dst1 ? dst1 + r0 * pitch : nullptr, pitch, p->padl);
+                if (plane_cs) split_colours_kernel<T><<<tg, tb, 0, ss.up>>>(plane + r0 * pitch, plane_cs + r0 * pitch, n_rows, pitch);
+                p->launches += plane_cs ? 2 : 1;
+                return APDE_OK;
+            };
+            APDE_TRY(one(grid, cols, n, false, p->U<T>(0), p->U<T>(1), nullptr, nullptr));
+            if (p->d.has_source) APDE_TRY(one(src, cols, n, false, p->S<T>(), nullptr, p->S<T>(), p->SC<T>()));
+            if (p->d.has_noise) {
+                APDE_TRY(one(nh, cols - 1, n, true, p->GH<T>(), nullptr, p->GH<T>(), p->GHC<T>()));
+                APDE_TRY(one(nv, cols, std::min<int64_t>(r1, rows - 1) - r0, true, p->GV<T>(), nullptr, p->GV<T>(), p->GVC<T>()));
+            }
+            APDE_CUDA(cudaGetLastError());
+        }
+        APDE_TRY(ss.event(&up_done[(size_t)c]));
+        APDE_CUDA(cudaEventRecord(up_done[(size_t)c], ss.up));
+        return APDE_OK;
+    };
+    auto run_band = [&](int64_t b) -> int {
+        APDE_CUDA(cudaStreamWaitEvent(ss.run, up_done[(size_t)std::min<int64_t>(b, nchunk - 1)], 0));
+        if (b == 0) APDE_CUDA(cudaEventRecord(t0, ss.run));
+        for (int64_t pass = 1; pass <= P; ++pass) {
+            const int64_t lo = band_edge(b, pass), hi = (b == nb - 1) ? rows : band_edge(b + 1, pass);
+            if (hi <= lo) continue;
+            const int td = (int)std::min<int64_t>(TD, n_sweeps - (pass - 1) * TD);
+            const int src_buf = (int)((pass - 1) % 2);
+            APDE_TRY(sizeof(T) == 8 ? run_stream_band_f64(p, td, (pass - 1) * TD, src_buf, lo, hi, rbh, ss.run)
+                                    : run_stream_band_f32(p, td, (pass - 1) * TD, src_buf, lo, hi, rbh, ss.run));
+        }
+        if (b == nb - 1) APDE_CUDA(cudaEventRecord(t1, ss.run));
+        APDE_TRY(ss.event(&band_done[(size_t)b]));
+        APDE_CUDA(cudaEventRecord(band_done[(size_t)b], ss.run));
+        return APDE_OK;
+    };
+    auto download_band = [&](int64_t b) -> int {
+        const int64_t lo = band_edge(b, P), hi = (b == nb - 1) ? rows : band_edge(b + 1, P);
+        if (hi <= lo) return APDE_OK;
+        APDE_CUDA(cudaStreamWaitEvent(ss.down, band_done[(size_t)b], 0));
+        unpack_kernel<T><<<tg, tb, 0, ss.down>>>(final_u, g, stage_dn, lo, hi - lo);
+        APDE_CUDA(cudaGetLastError());
+        APDE_CUDA(cudaMemcpyAsync(grid + (size_t)lo * (size_t)cols, stage_dn, (size_t)(hi - lo) * (size_t)cols * 8,
+                                  cudaMemcpyDeviceToHost, ss.down));
+        p->launches += 1;
+        return APDE_OK;
+    };
+    for (int64_t i = 0; i <= std::max(nchunk, nb); ++i) {
+        if (i < nchunk) APDE_TRY(upload_chunk(i));
+        if (i < nb) APDE_TRY(run_band(i));
+        if (i >= 1 && i - 1 < nb) APDE_TRY(download_band(i - 1));
+    }
+    APDE_CUDA(cudaStreamSynchronize(ss.up));
+    APDE_CUDA(cudaStreamSynchronize(ss.run));
+    APDE_CUDA(cudaStreamSynchronize(ss.down));
+    APDE_CUDA(cudaGetLastError());
+    APDE_CUDA(cudaEventElapsedTime(kernel_ms, t0, t1));
+    p->cur = final_buf;
+    p->pass_open = false;
+    p->filled = true;
+    p->split_dirty = false;
+    return APDE_OK;
+}
+
 int solve_redblack(int elem, double *grid, const double *nh, const double *nv, const double *src,
                    int64_t rows, int64_t cols, double tol, int64_t max_iter, int check_every,
                    int temporal_depth, double *hist, int64_t *iters, double *ksec, double omega, bool kcl) {
@@ -882,6 +1058,27 @@ int solve_redblack(int elem, double *grid, const double *nh, const double *nv, c
     } guard{p, use_cache};
     p->omega = omega;
     p->kcl = kcl;
+    // fixed-sweep runs of the fused streaming kernel on grids worth it: upload, sweeps and download overlap
+    {
+        int64_t band = 1536, rbh = 192;  // 8 row blocks x column strips = one wave of the resident warps at 16384 columns (tools/e2e_stream_sweep.py)
+        if (const char *v = getenv("APDE_STREAM_BAND")) band = std::max<int64_t>(64, atoll(v));
+        if (const char *v = getenv("APDE_STREAM_RBH")) rbh = std::max<int64_t>(8, atoll(v));
+        const char *sw = getenv("APDE_STREAMED");  // "0": never, "1": whenever valid (tests), unset: large grids
+        const bool valid = !(tol > 0.0) && omega == 1.0 && !kcl && p->variant == 1 && rows >= 2 * band && band >= 4 * 2 * (int64_t)temporal_depth;
+        const bool want = sw ? atoi(sw) != 0 : rows * cols >= (int64_t)1 << 24;
+        if (valid && want) {
+            float ms = 0.f;
+            APDE_TRY(elem == 8 ? solve_streamed_t<double>(p, grid, nh, nv, src, max_iter, band, rbh, &ms)
+                               : solve_streamed_t<float>(p, grid, nh, nv, src, max_iter, band, rbh, &ms));
+            APDE_TRY(plan_read_residuals(p, 0, max_iter, hist, 0));
+            *iters = max_iter;
+            if (ksec) *ksec = ms * 1e-3;
+            if (trace)
+                fprintf(stderr, "[apde] solve_redblack %lldx%lld streamed: create %.1f ms, upload + %lld sweeps + download %.1f ms (first to last pass %.1f ms)\n",
+                        (long long)rows, (long long)cols, (t_created - t_begin) * 1e3, (long long)max_iter, (now() - t_created) * 1e3, ms);
+            return APDE_OK;
+        }
+    }
     APDE_TRY(plan_upload(p, grid, nh, nv, src));
     const double t_uploaded = now();
     // ---- sweep loop without host round trips -------------------------------------------------------------

@@ -530,7 +530,8 @@ def run_ours(args):
             def e2e_step():
                 _backend.solve(mode, host_u, host_nh, host_nv, host_s, 0.0, K, check_every=32,
                                temporal_depth=args.depth)
-            api = f"apde_solve_redblack_{args.dtype} (one call = upload + {K} sweeps, residuals checked every 32 + download)"
+            api = (f"apde_solve_redblack_{args.dtype} (one call = upload + {K} sweeps + download; fixed sweep count, so the call streams: "
+                   "upload chunks, parallelogram-tiled passes band by band and the download of finished bands overlap)")
         else:
             out_host = pin((owned, args.cols))
             d2h = out_host.nbytes + K * 8

@@ -402,3 +402,48 @@ def test_device_side_stop_semantics(mode, dt, check_every, depth):
     g = g0.copy()
     hist, n, _ = _backend.solve(mode, g, nh, nv, s, 1e-300, 37, check_every=check_every, temporal_depth=depth)
     assert n == 37 and len(hist) == 37
+
+
+@pytest.mark.parametrize("rows,cols,k,depth,band,rbh", [
+    (700, 300, 37, 4, 64, 16),    # 10 passes (the last of one sweep), 17 bands incl. the ones that exist only for late passes
+    (515, 129, 24, 3, 128, 32),   # depth 3: 6-row shift per pass, 8 passes
+    (300, 1000, 9, 4, 96, 96),    # band = one row block; 3 passes (4 + 4 + 1 sweeps)
+    (2100, 260, 130, 4, 256, 64), # 33 passes: the shift (256 rows) reaches a whole band
+])
+@pytest.mark.parametrize("mode,sigma,src", [("redblack", 0.01, True), ("redblack", 0.0, True), ("redblack32", 0.01, False)])
+def test_streamed_solve_equals_unstreamed_bitwise(rows, cols, k, depth, band, rbh, mode, sigma, src, monkeypatch):
+    """The streamed one-shot solve (upload chunks, parallelogram-tiled passes band by band, download of finished bands, all
+    overlapping) returns the same grid and residual history as upload -> all passes -> download, bit for bit; the
+    unstreamed path is the one compared with the CPU oracle above."""
+    g0, nh, nv, s = random_problem(rows, cols, sigma, seed=rows + k, with_source=src)
+    out = {}
+    for streamed in ("0", "1"):
+        monkeypatch.setenv("APDE_STREAMED", streamed)
+        monkeypatch.setenv("APDE_STREAM_BAND", str(band))
+        monkeypatch.setenv("APDE_STREAM_RBH", str(rbh))
+        g = g0.copy()
+        hist, n, _ = _backend.solve(mode, g, nh, nv, s, 0.0, k, temporal_depth=depth)
+        assert n == k
+        out[streamed] = (g, hist)
+    assert out["0"][0].tobytes() == out["1"][0].tobytes()
+    assert out["0"][1].tobytes() == out["1"][1].tobytes()
+    assert not np.array_equal(out["1"][0], g0)
+
+
+def test_streamed_solve_vs_oracle_and_tolerance_runs_stay_unstreamed(monkeypatch):
+    """Streamed result against the CPU statement directly; a run with tol > 0 never takes the streamed path (its stop
+    decision needs whole-grid residuals sweep by sweep) and stops where it always did."""
+    monkeypatch.setenv("APDE_STREAMED", "1")
+    monkeypatch.setenv("APDE_STREAM_BAND", "64")
+    monkeypatch.setenv("APDE_STREAM_RBH", "32")
+    g0, nh, nv, s = random_problem(400, 210, 0.01, seed=3, with_source=True)
+    ru, rh, _ = oracle.red_black(g0, nh, nv, s, 21)
+    g = g0.copy()
+    hist, n, _ = _backend.solve("redblack", g, nh, nv, s, 0.0, 21, temporal_depth=4)
+    assert n == 21 and g.tobytes() == ru.tobytes() and hist.tobytes() == rh.tobytes()
+    g = g0.copy()
+    hist, n, _ = _backend.solve("redblack", g, nh, nv, s, 1e-3, 4000, check_every=8, temporal_depth=4)
+    monkeypatch.setenv("APDE_STREAMED", "0")
+    g2 = g0.copy()
+    hist2, n2, _ = _backend.solve("redblack", g2, nh, nv, s, 1e-3, 4000, check_every=8, temporal_depth=4)
+    assert n == n2 < 4000 and g.tobytes() == g2.tobytes() and hist.tobytes() == hist2.tobytes()
