@@ -855,12 +855,12 @@ __global__ void pack_rows_kernel(const double *__restrict__ in, long long nrows,
 }
 
 struct StreamSet {
-    cudaStream_t up = nullptr, run = nullptr, down = nullptr;
+    cudaStream_t up = nullptr, run = nullptr, run2 = nullptr, down = nullptr;
     std::vector<cudaEvent_t> ev;
     ~StreamSet() {
         for (auto e : ev)
             if (e) cudaEventDestroy(e);
-        for (auto s : {up, run, down})
+        for (auto s : {up, run, run2, down})
             if (s) cudaStreamDestroy(s);
     }
     int event(cudaEvent_t *out) {
@@ -880,10 +880,30 @@ static int solve_streamed_t(apde_plan *p, double *grid, const double *nh, const 
     const int TD = std::min(p->d.temporal_depth, 4);
     const int64_t h = 2 * TD, P = (n_sweeps + TD - 1) / TD;
     const int64_t skew_max = (P - 1) * h;
-    const int64_t nb = (rows + skew_max + B - 1) / B;  // bands: the last ones exist only for the late (far shifted) passes
-    const int64_t nchunk = (rows + B - 1) / B + 1;
-    auto chunk_edge = [&](int64_t c) { return c <= 0 ? (int64_t)0 : std::min<int64_t>(rows, c * B + h); };  // rows < (b+1)*B + h feed band b
-    auto band_edge = [&](int64_t b, int64_t pass /*1-based*/) { return std::min<int64_t>(rows, std::max<int64_t>(0, b * B - (pass - 1) * h)); };
+    // Unshifted band edges.  Bands are B rows, except that the first two (B/4, B/2) let the sweeps start after a small
+    // upload and the last two (B/2, B/4) leave a small download behind the last pass; together they cover rows + the
+    // largest shift (the last bands exist only for the late, far shifted passes).
+    std::vector<int64_t> edge0{0};
+    {
+        const int64_t q = std::max<int64_t>(4 * h, (B / 4) & ~(int64_t)7), hq = std::max<int64_t>(4 * h, (B / 2) & ~(int64_t)7);
+        const int64_t need = rows + skew_max;
+        int64_t n_full = (need - 2 * (q + hq) + B - 1) / B;
+        if (n_full < 0) n_full = 0;
+        std::vector<int64_t> sizes{q, hq};
+        for (int64_t k = 0; k < n_full; ++k) sizes.push_back(B);
+        sizes.push_back(hq);
+        sizes.push_back(q);
+        for (int64_t sz : sizes) {
+            if (edge0.back() >= need) break;
+            edge0.push_back(edge0.back() + sz);
+        }
+    }
+    const int64_t nb = (int64_t)edge0.size() - 1, nchunk = nb;
+    // chunk c = the rows band c needs beyond chunk c-1 (band b reads rows < edge0[b+1] + h in its first pass)
+    auto chunk_edge = [&](int64_t c) { return c <= 0 ? (int64_t)0 : std::min<int64_t>(rows, edge0[(size_t)std::min<int64_t>(c, nb)] + h); };
+    auto band_edge = [&](int64_t b, int64_t pass /*1-based*/) {
+        return std::min<int64_t>(rows, std::max<int64_t>(0, edge0[(size_t)std::min<int64_t>(b, nb)] - (pass - 1) * h));
+    };
 
     // staging: one chunk going up, one band coming down
     const size_t up_rows = (size_t)(B + h), stage_elems = (up_rows + (size_t)B) * (size_t)cols;
@@ -904,11 +924,27 @@ static int solve_streamed_t(apde_plan *p, double *grid, const double *nh, const 
     APDE_CUDA(cudaDeviceSynchronize());  // the legacy stream may still hold work on these buffers
 
     StreamSet ss;
-    APDE_CUDA(cudaStreamCreateWithFlags(&ss.up, cudaStreamNonBlocking));
-    APDE_CUDA(cudaStreamCreateWithFlags(&ss.run, cudaStreamNonBlocking));
-    APDE_CUDA(cudaStreamCreateWithFlags(&ss.down, cudaStreamNonBlocking));
-    const int tb = 256, tg = p->sm_count * 8;
+    // the sweeps are the critical path: their stream gets the highest priority, and the conversion kernels of the copy
+    // streams (which only have to keep up with PCIe) run on one small CTA per SM beside the two resident sweep CTAs
+    int prio_lo = 0, prio_hi = 0;
+    APDE_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    APDE_CUDA(cudaStreamCreateWithPriority(&ss.up, cudaStreamNonBlocking, prio_lo));
+    APDE_CUDA(cudaStreamCreateWithPriority(&ss.run, cudaStreamNonBlocking, prio_hi));
+    APDE_CUDA(cudaStreamCreateWithPriority(&ss.run2, cudaStreamNonBlocking, prio_hi));
+    APDE_CUDA(cudaStreamCreateWithPriority(&ss.down, cudaStreamNonBlocking, prio_lo));
+    int tg = p->sm_count * 8;
+    if (const char *v = getenv("APDE_STREAM_COPY_CTAS")) tg = std::max(1, atoi(v));
+    // Two compute lanes: band b runs on lane b % 2, pass p of it behind pass p-1 of band b-1 on the other lane (an event
+    // per pass) -- the only dependence between neighbouring bands -- so the last warps of one launch overlap the first
+    // of an independent one instead of an idle tail (every launch is a single wave of warps).
+    int lanes = 2;
+    if (const char *v = getenv("APDE_STREAM_LANES")) lanes = atoi(v) >= 2 ? 2 : 1;
+    const int tb = 256;
     APDE_CUDA(cudaMemsetAsync(p->resid.as<T>(), 0, (size_t)n_sweeps * sizeof(T), ss.run));
+    cudaEvent_t resid_cleared;
+    APDE_TRY(ss.event(&resid_cleared));
+    APDE_CUDA(cudaEventRecord(resid_cleared, ss.run));
+    APDE_CUDA(cudaStreamWaitEvent(ss.run2, resid_cleared, 0));
 
     // ---- one loop queues chunk i (upload stream), band i (compute stream) and the download of band i-1 ------------
     // (all asynchronous from pinned host memory; with pageable memory the copies block the host, and this order keeps
@@ -952,20 +988,35 @@ static int solve_streamed_t(apde_plan *p, double *grid, const double *nh, const 
         APDE_CUDA(cudaEventRecord(up_done[(size_t)c], ss.up));
         return APDE_OK;
     };
+    std::vector<cudaEvent_t> pass_done[2];  // per pass: the previous band's / this band's
+    pass_done[0].assign((size_t)P + 1, nullptr);
+    pass_done[1].assign((size_t)P + 1, nullptr);
     auto run_band = [&](int64_t b) -> int {
-        APDE_CUDA(cudaStreamWaitEvent(ss.run, up_done[(size_t)std::min<int64_t>(b, nchunk - 1)], 0));
-        if (b == 0) APDE_CUDA(cudaEventRecord(t0, ss.run));
+        cudaStream_t st = (lanes == 2 && (b & 1)) ? ss.run2 : ss.run;
+        std::vector<cudaEvent_t> &prev = pass_done[(b + 1) & 1], &mine = pass_done[b & 1];
+        APDE_CUDA(cudaStreamWaitEvent(st, up_done[(size_t)std::min<int64_t>(b, nchunk - 1)], 0));
+        if (b == 0) APDE_CUDA(cudaEventRecord(t0, st));
         for (int64_t pass = 1; pass <= P; ++pass) {
             const int64_t lo = band_edge(b, pass), hi = (b == nb - 1) ? rows : band_edge(b + 1, pass);
-            if (hi <= lo) continue;
-            const int td = (int)std::min<int64_t>(TD, n_sweeps - (pass - 1) * TD);
-            const int src_buf = (int)((pass - 1) % 2);
-            APDE_TRY(sizeof(T) == 8 ? run_stream_band_f64(p, td, (pass - 1) * TD, src_buf, lo, hi, rbh, ss.run)
-                                    : run_stream_band_f32(p, td, (pass - 1) * TD, src_buf, lo, hi, rbh, ss.run));
+            if (lanes == 2 && b > 0 && pass > 1) APDE_CUDA(cudaStreamWaitEvent(st, prev[(size_t)pass - 1], 0));
+            if (hi > lo) {
+                const int td = (int)std::min<int64_t>(TD, n_sweeps - (pass - 1) * TD);
+                const int src_buf = (int)((pass - 1) % 2);
+                // a clipped band (the top band shrinks with every pass, the bottom ones grow) is still cut into the same
+                // NUMBER of row blocks: the launch stays one full wave of warps and simply ends sooner
+                const int64_t nblk = std::max<int64_t>(1, B / rbh);
+                const int64_t rbh_l = std::min<int64_t>(rbh, std::max<int64_t>(32, (hi - lo + nblk - 1) / nblk));
+                APDE_TRY(sizeof(T) == 8 ? run_stream_band_f64(p, td, (pass - 1) * TD, src_buf, lo, hi, rbh_l, st)
+                                        : run_stream_band_f32(p, td, (pass - 1) * TD, src_buf, lo, hi, rbh_l, st));
+            }
+            if (lanes == 2) {
+                if (!mine[(size_t)pass]) APDE_TRY(ss.event(&mine[(size_t)pass]));  // slots are reused two bands on: the band in
+                APDE_CUDA(cudaEventRecord(mine[(size_t)pass], st));                // between has consumed them (stream order)
+            }
         }
-        if (b == nb - 1) APDE_CUDA(cudaEventRecord(t1, ss.run));
+        if (b == nb - 1) APDE_CUDA(cudaEventRecord(t1, st));
         APDE_TRY(ss.event(&band_done[(size_t)b]));
-        APDE_CUDA(cudaEventRecord(band_done[(size_t)b], ss.run));
+        APDE_CUDA(cudaEventRecord(band_done[(size_t)b], st));
         return APDE_OK;
     };
     auto download_band = [&](int64_t b) -> int {
@@ -986,6 +1037,7 @@ static int solve_streamed_t(apde_plan *p, double *grid, const double *nh, const 
     }
     APDE_CUDA(cudaStreamSynchronize(ss.up));
     APDE_CUDA(cudaStreamSynchronize(ss.run));
+    APDE_CUDA(cudaStreamSynchronize(ss.run2));
     APDE_CUDA(cudaStreamSynchronize(ss.down));
     APDE_CUDA(cudaGetLastError());
     APDE_CUDA(cudaEventElapsedTime(kernel_ms, t0, t1));
