@@ -71,6 +71,12 @@ int apde_solve_exact_f64_path(double *grid, const double *noise_h, const double 
  *   _f64: fp64 arithmetic;  _f32: fp32 arithmetic (host arrays stay float64, converted on device).
  * check_every <= 0 => 32; temporal_depth <= 0 => library default (4); values above the
  * kernel family's maximum (4; 6 for APDE_RB_VARIANT=v2) are clamped.
+ * A call that cannot stop early (tol <= 0, i.e. exactly max_iter sweeps) on a grid of >= 2^24 nodes is STREAMED:
+ * the host arrays go up in row chunks, the fused passes follow the upload front band by band (parallelogram tiling:
+ * the bands of pass p are shifted up by (p-1)*2*temporal_depth rows) and finished bands come back while later ones
+ * are still relaxed -- same grid and residual history bit for bit, about half the wall time from pinned host memory.
+ * Environment: APDE_STREAMED=0 never / 1 whenever valid; APDE_STREAM_BAND, APDE_STREAM_RBH (rows per band / row block),
+ * APDE_STREAM_LANES (1 or 2 compute streams).
  * ---------------------------------------------------------------------------------------- */
 int apde_solve_redblack_f64(double *grid, const double *noise_h, const double *noise_v,
                             const double *source, int64_t rows, int64_t cols, double tol,
