@@ -52,11 +52,10 @@ struct StreamArgs {
     T *resid;  // slot of the first sweep of this pass
     const int *stop;  // optional device flag: set => the solve has converged, do nothing
     long long pitch, padl, lrows, cols, grows, row0;
-    // two groups of row blocks: blk_an blocks of rbh rows cut from the local rows [own_lo, own_hi), then blk_bn blocks of
-    // rbh_b rows cut from [lo_b, hi_b) -- a whole strip is one group; the strip-edge phase of a multi-GPU pass is one short
-    // block per side, the interior phase the rows in between
-    long long own_lo, own_hi, rbh, blk_an;
-    long long lo_b, hi_b, rbh_b, blk_bn;
+    long long own_lo, own_hi;      // the local rows this launch cuts into row blocks (a strip, a strip-edge or interior region, a band)
+    long long rbh;                 // row-block height
+    long long blk_a0, blk_an;      // row blocks [blk_a0, blk_a0+blk_an) ...
+    long long blk_b0, blk_bn;      // ... and [blk_b0, blk_b0+blk_bn)
     long long n_strips, n_items;
 };
 
@@ -384,11 +383,10 @@ __global__ void __launch_bounds__(RBS_THREADS, rbs_min_blocks((int)sizeof(T), C,
     for (long long item = warp_id; item < a.n_items; item += n_warps) {
         const long long bsel = item / a.n_strips;
         const long long sidx = item - bsel * a.n_strips;
-        const bool grp_a = bsel < a.blk_an;
-        const long long blk = grp_a ? bsel : bsel - a.blk_an, bh = grp_a ? a.rbh : a.rbh_b;
+        const long long blk = bsel < a.blk_an ? a.blk_a0 + bsel : a.blk_b0 + (bsel - a.blk_an);
         // local row indices fit 32 bits; only element offsets are 64-bit (carried in the pointers)
-        const int rb0 = (int)((grp_a ? a.own_lo : a.lo_b) + blk * bh);
-        const int rb1 = (int)min((long long)rb0 + bh, grp_a ? a.own_hi : a.hi_b);
+        const int rb0 = (int)(a.own_lo + blk * a.rbh);
+        const int rb1 = (int)min((long long)rb0 + a.rbh, a.own_hi);
         const long long jl0 = sidx * VW - HCA + (long long)C * lane;  // first column of this lane (even)
         const bool lane_valid = (C * lane >= HCA) && (C * lane < CW - HCA) && (jl0 < a.cols);
         unsigned colmask = 0;  // bit q: column jl0+q is an interior column
@@ -811,43 +809,38 @@ int launch_pass(apde_plan *p, StreamArgs &a, const BlockReq &rq, cudaStream_t st
     // the same function of the input buffer).
     const long long own_lo = a.own_lo, own_hi = a.own_hi;
     const long long eh = rq.forced_rbh > 0 ? std::max(rq.forced_rbh, rq.halo) : std::max<long long>(rq.halo, 64);
-    long long et = rq.top_nb ? eh : 0, eb = rq.bot_nb ? eh : 0;
+    const long long et = rq.top_nb ? eh : 0, eb = rq.bot_nb ? eh : 0;
     const bool split = rq.phase != 0 && et + eb > 0 && et + eb < rq.owned;  // else: phase 1 takes the whole strip
-    a.blk_an = a.blk_bn = 0;
-    a.lo_b = a.hi_b = own_hi;
-    a.rbh = a.rbh_b = 1;
-    if (rq.band_hi > rq.band_lo) {
-        a.own_lo = rq.band_lo;
-        a.own_hi = rq.band_hi;
-        a.rbh = std::max<long long>(rq.band_rbh, 8);
-        a.blk_an = (rq.band_hi - rq.band_lo + a.rbh - 1) / a.rbh;
-    } else if (rq.phase == 1 && split) {
-        a.own_hi = own_lo + et;
-        a.rbh = std::max<long long>(et, 1);
-        a.blk_an = et > 0 ? 1 : 0;
-        a.lo_b = own_hi - eb;
-        a.rbh_b = std::max<long long>(eb, 1);
-        a.blk_bn = eb > 0 ? 1 : 0;
-    } else if (rq.phase == 2 && !split) {
-        return APDE_OK;  // phase 1 did everything
-    } else {
-        if (rq.phase == 2) {
-            a.own_lo = own_lo + et;
-            a.own_hi = own_hi - eb;
-        }
-        const long long rows = a.own_hi - a.own_lo;
-        a.rbh = rq.forced_rbh > 0 ? std::max(rq.forced_rbh, rq.halo) : pick_row_block(rows, a.n_strips, resident_warps, 2 * TD, rq.halo);
-        a.blk_an = (rows + a.rbh - 1) / a.rbh;
+    // one launch over the local rows [lo, hi) in blocks of `bh` rows (the kernel itself is the round-2 one: its row-block
+    // prologue is left alone -- a two-origin variant of it cost the fp64 Poisson instantiation 5 %)
+    auto launch = [&](long long lo, long long hi, long long bh) -> int {
+        if (hi <= lo) return APDE_OK;
+        a.own_lo = lo;
+        a.own_hi = hi;
+        a.rbh = std::max<long long>(bh, 1);
+        a.blk_a0 = 0;
+        a.blk_an = (hi - lo + a.rbh - 1) / a.rbh;
+        a.blk_b0 = a.blk_bn = 0;
+        a.n_items = a.blk_an * a.n_strips;
+        long long grid = (long long)p->sm_count * blocks_per_sm;
+        const long long need = (a.n_items + warps_per_block - 1) / warps_per_block;
+        if (grid > need) grid = need;
+        if (grid < 1) grid = 1;
+        rb_stream_kernel<C, TD, NOISE, SRC><<<(unsigned)grid, RBS_THREADS, smem, st>>>(a);
+        p->launches++;
+        return APDE_OK;
+    };
+    auto best_height = [&](long long rows) {
+        return rq.forced_rbh > 0 ? std::max(rq.forced_rbh, rq.halo) : pick_row_block(rows, a.n_strips, resident_warps, 2 * TD, rq.halo);
+    };
+    if (rq.band_hi > rq.band_lo) return launch(rq.band_lo, rq.band_hi, std::max<long long>(rq.band_rbh, 8));
+    if (rq.phase == 1 && split) {  // one short block per side with a neighbour (two small launches)
+        APDE_TRY(launch(own_lo, own_lo + et, et));
+        return launch(own_hi - eb, own_hi, eb);
     }
-    a.n_items = (a.blk_an + a.blk_bn) * a.n_strips;
-    if (a.n_items <= 0) return APDE_OK;
-    long long grid = (long long)p->sm_count * blocks_per_sm;
-    const long long need = (a.n_items + warps_per_block - 1) / warps_per_block;
-    if (grid > need) grid = need;
-    if (grid < 1) grid = 1;
-    rb_stream_kernel<C, TD, NOISE, SRC><<<(unsigned)grid, RBS_THREADS, smem, st>>>(a);
-    p->launches++;
-    return APDE_OK;
+    if (rq.phase == 2 && !split) return APDE_OK;  // phase 1 did everything
+    if (rq.phase == 2) return launch(own_lo + et, own_hi - eb, best_height(own_hi - eb - own_lo - et));
+    return launch(own_lo, own_hi, best_height(own_hi - own_lo));
 }
 
 template <int C, bool NOISE, bool SRC>
