@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = (
     "apde_plan_create", "apde_plan_destroy", "apde_plan_upload", "apde_plan_upload_rows", "apde_plan_download_rows", "apde_plan_fill",
     "apde_plan_download", "apde_plan_clear_residuals", "apde_plan_run", "apde_plan_halo", "apde_plan_residuals",
     "apde_plan_read_residuals", "apde_plan_launch_count", "apde_plan_checksum", "apde_plan_checksum_bits", "apde_memcpy_dtod", "apde_selftest_division", "apde_plan_energy_sums", "apde_plan_download_array", "apde_default_temporal_depth", "apde_solve_redblack_ex", "apde_plan_set_relaxation",
-    "apde_solve_multigrid", "apde_multigrid_levels",
+    "apde_solve_multigrid", "apde_multigrid_levels", "apde_solve_redblack_window",
 )
 
 
@@ -81,6 +81,8 @@ def load():
     lib.apde_solve_redblack_multi.restype = ctypes.c_int
     lib.apde_solve_redblack_multi.argtypes = [ctypes.c_int, _dp, _dp, _dp, _dp] + solve_tail + [
         ctypes.c_int, ctypes.c_int, ctypes.c_int, _dp, _i64p, _dp]
+    lib.apde_solve_redblack_window.restype = ctypes.c_int
+    lib.apde_solve_redblack_window.argtypes = [ctypes.c_int, _dp, _dp, _dp, _dp, _i64, _i64, _i64, ctypes.c_int, _i64, _i64, _dp, _dp]
     lib.apde_plan_create.restype = ctypes.c_int
     lib.apde_plan_create.argtypes = [ctypes.POINTER(_vp), ctypes.POINTER(PlanDesc)]
     lib.apde_plan_destroy.restype = ctypes.c_int
@@ -225,6 +227,27 @@ def _solve_once(lib, mode, grid, nh, nv, src, tol, max_iter, check_every, tempor
     check(rc)
     n = int(iters.value)
     return hist[:max(n, 0)], n, float(ksec.value)
+
+
+def solve_window(mode: str, grid: np.ndarray, noise_h, noise_v, source, n_sweeps: int, win_lo: int, win_hi: int,
+                 temporal_depth: int = 0):
+    """apde_solve_redblack_window: exactly n_sweeps red-black sweeps of `grid` (in place, rows [win_lo, win_hi) only are
+    written back), residual history over the window rows.  Returns (hist, kernel_seconds)."""
+    lib = load()
+    if mode not in ("redblack", "redblack64", "redblack32"):
+        raise ValueError(f"solve_window: mode must be redblack or redblack32, got {mode!r}")
+    if grid.dtype != np.float64 or not grid.flags.c_contiguous or grid.ndim != 2:
+        raise ValueError("grid must be a C-contiguous float64 2-D array")
+    rows, cols = grid.shape
+    nh = _as_f64(noise_h, (rows, cols - 1), "noise_h")
+    nv = _as_f64(noise_v, (rows - 1, cols), "noise_v")
+    src = _as_f64(source, (rows, cols), "source")
+    hist = np.zeros(max(int(n_sweeps), 1), dtype=np.float64)
+    ksec = ctypes.c_double(0.0)
+    check(lib.apde_solve_redblack_window(4 if mode == "redblack32" else 8, _ptr(grid), _ptr(nh), _ptr(nv), _ptr(src), rows, cols,
+                                         int(n_sweeps), int(temporal_depth), int(win_lo), int(win_hi), _ptr(hist),
+                                         ctypes.byref(ksec)))
+    return hist[:max(int(n_sweeps), 0)], float(ksec.value)
 
 
 def solve(mode: str, grid: np.ndarray, noise_h, noise_v, source, tol: float, max_iter: int,

@@ -125,6 +125,21 @@ int apde_solve_redblack_f32(double *grid, const double *noise_h, const double *n
                           temporal_depth, residual_history, iterations_run, kernel_seconds);
 }
 
+int apde_solve_redblack_window(int dtype_bytes, double *grid, const double *noise_h, const double *noise_v,
+                               const double *source, int64_t rows, int64_t cols, int64_t n_sweeps, int temporal_depth,
+                               int64_t win_lo, int64_t win_hi, double *residual_history, double *kernel_seconds) {
+    int64_t dummy = 0;
+    APDE_TRY(check_solve_args("apde_solve_redblack_window", grid, noise_h, noise_v, rows, cols, n_sweeps,
+                              residual_history, &dummy));
+    if (dtype_bytes != 4 && dtype_bytes != 8) {
+        set_error("apde_solve_redblack_window: dtype_bytes must be 4 or 8");
+        return APDE_EINVAL;
+    }
+    std::lock_guard<std::mutex> lock(g_solve_mutex);
+    return solve_redblack_window(dtype_bytes, grid, noise_h, noise_v, source, rows, cols, n_sweeps, temporal_depth,
+                                 win_lo, win_hi, residual_history, kernel_seconds);
+}
+
 int apde_solve_redblack_multi(int dtype_bytes, double *grid, const double *noise_h, const double *noise_v,
                               const double *source, int64_t rows, int64_t cols, double tol,
                               int64_t max_iter, int check_every, int temporal_depth, int n_gpus,

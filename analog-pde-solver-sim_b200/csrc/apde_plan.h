@@ -86,6 +86,9 @@ int solve_redblack(int elem, double *grid, const double *nh, const double *nv, c
                    int64_t rows, int64_t cols, double tol, int64_t max_iter, int check_every,
                    int temporal_depth, double *hist, int64_t *iters, double *ksec, double omega = 1.0,
                    bool kcl = false);
+int solve_redblack_window(int elem, double *grid, const double *nh, const double *nv, const double *src, int64_t rows,
+                          int64_t cols, int64_t n_sweeps, int temporal_depth, int64_t win_lo, int64_t win_hi, double *hist,
+                          double *ksec);
 int plan_set_relaxation(apde_plan *p, double omega, int normalised);
 // implemented in apde_multigrid.cu
 int mg_level_count(int64_t rows, int64_t cols);

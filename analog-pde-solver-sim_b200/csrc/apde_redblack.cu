@@ -874,12 +874,16 @@ struct StreamSet {
 
 template <typename T>
 static int solve_streamed_t(apde_plan *p, double *grid, const double *nh, const double *nv, const double *src,
-                            int64_t n_sweeps, int64_t B, int64_t rbh, float *kernel_ms) {
+                            int64_t n_sweeps, int64_t B, int64_t rbh, float *kernel_ms, int64_t win_lo = 0, int64_t win_hi = -1) {
     const Geo g = make_geo(p);
     const int64_t rows = p->d.grows, cols = p->d.cols, pitch = p->pitch;
     const int TD = std::min(p->d.temporal_depth, 4);
     const int64_t h = 2 * TD, P = (n_sweeps + TD - 1) / TD;
     const int64_t skew_max = (P - 1) * h;
+    // result window (apde_solve_redblack_window): residuals are taken over, and the grid is written back for, the rows
+    // [win_lo, win_hi) only; launches are cut at the window edges and the pieces outside report into a dump area
+    if (win_hi < 0) win_hi = rows;
+    const bool windowed = win_lo > 0 || win_hi < rows;
     // Unshifted band edges.  Bands are B rows, except that the first two (B/4, B/2) let the sweeps start after a small
     // upload and the last two (B/2, B/4) leave a small download behind the last pass; together they cover rows + the
     // largest shift (the last bands exist only for the late, far shifted passes).
@@ -920,7 +924,7 @@ static int solve_streamed_t(apde_plan *p, double *grid, const double *nh, const 
     APDE_TRY(ensure_plane(p->src, p->src_cs));
     APDE_TRY(ensure_plane(p->gh, p->gh_cs));
     APDE_TRY(ensure_plane(p->gv, p->gv_cs));
-    APDE_TRY(plan_ensure_resid(p, n_sweeps));
+    APDE_TRY(plan_ensure_resid(p, windowed ? 2 * n_sweeps : n_sweeps));  // second half: the dump area
     APDE_CUDA(cudaDeviceSynchronize());  // the legacy stream may still hold work on these buffers
 
     StreamSet ss;
@@ -1006,8 +1010,14 @@ static int solve_streamed_t(apde_plan *p, double *grid, const double *nh, const 
                 // NUMBER of row blocks: the launch stays one full wave of warps and simply ends sooner
                 const int64_t nblk = std::max<int64_t>(1, B / rbh);
                 const int64_t rbh_l = std::min<int64_t>(rbh, std::max<int64_t>(32, (hi - lo + nblk - 1) / nblk));
-                APDE_TRY(sizeof(T) == 8 ? run_stream_band_f64(p, td, (pass - 1) * TD, src_buf, lo, hi, rbh_l, st)
-                                        : run_stream_band_f32(p, td, (pass - 1) * TD, src_buf, lo, hi, rbh_l, st));
+                const int64_t cuts[4] = {lo, std::min(std::max(win_lo, lo), hi), std::max(std::min(win_hi, hi), lo), hi};
+                for (int k = 0; k < 3; ++k) {  // above the window / inside / below (one piece unless windowed)
+                    const int64_t plo = cuts[k], phi = cuts[k + 1];
+                    if (phi <= plo) continue;
+                    const int64_t slot = (pass - 1) * TD + (k == 1 ? 0 : n_sweeps);
+                    APDE_TRY(sizeof(T) == 8 ? run_stream_band_f64(p, td, slot, src_buf, plo, phi, rbh_l, st)
+                                            : run_stream_band_f32(p, td, slot, src_buf, plo, phi, rbh_l, st));
+                }
             }
             if (lanes == 2) {
                 if (!mine[(size_t)pass]) APDE_TRY(ss.event(&mine[(size_t)pass]));  // slots are reused two bands on: the band in
@@ -1020,7 +1030,7 @@ static int solve_streamed_t(apde_plan *p, double *grid, const double *nh, const 
         return APDE_OK;
     };
     auto download_band = [&](int64_t b) -> int {
-        const int64_t lo = band_edge(b, P), hi = (b == nb - 1) ? rows : band_edge(b + 1, P);
+        const int64_t lo = std::max(win_lo, band_edge(b, P)), hi = std::min(win_hi, (b == nb - 1) ? rows : band_edge(b + 1, P));
         if (hi <= lo) return APDE_OK;
         APDE_CUDA(cudaStreamWaitEvent(ss.down, band_done[(size_t)b], 0));
         unpack_kernel<T><<<tg, tb, 0, ss.down>>>(final_u, g, stage_dn, lo, hi - lo);
@@ -1045,6 +1055,64 @@ static int solve_streamed_t(apde_plan *p, double *grid, const double *nh, const 
     p->pass_open = false;
     p->filled = true;
     p->split_dirty = false;
+    return APDE_OK;
+}
+
+// Fixed sweep count, result window: see include/apde.h (apde_solve_redblack_window).
+int solve_redblack_window(int elem, double *grid, const double *nh, const double *nv, const double *src, int64_t rows,
+                          int64_t cols, int64_t n_sweeps, int temporal_depth, int64_t win_lo, int64_t win_hi, double *hist,
+                          double *ksec) {
+    if (ksec) *ksec = 0.0;
+    if (temporal_depth <= 0) temporal_depth = default_temporal_depth(elem, nh != nullptr);
+    temporal_depth = std::min(std::min(temporal_depth, max_temporal_depth()), 4);
+    int64_t band = 1536, rbh = 192;
+    if (const char *v = getenv("APDE_STREAM_BAND")) band = std::max<int64_t>(64, atoll(v));
+    if (const char *v = getenv("APDE_STREAM_RBH")) rbh = std::max<int64_t>(8, atoll(v));
+    if (rows < 2 * band || band < 8 * (int64_t)temporal_depth || cols < 3 || n_sweeps <= 0 || win_lo < 0 || win_hi > rows || win_lo >= win_hi) {
+        set_error("solve_redblack_window: needs rows >= %lld (two bands), n_sweeps > 0 and 0 <= win_lo < win_hi <= rows", (long long)(2 * band));
+        return APDE_EINVAL;
+    }
+    apde_plan_desc d{};
+    d.dtype_bytes = elem;
+    d.has_noise = (nh != nullptr);
+    d.has_source = (src != nullptr);
+    d.temporal_depth = temporal_depth;
+    d.grows = rows;
+    d.cols = cols;
+    d.row_begin = 0;
+    d.row_end = rows;
+    apde_plan *p = nullptr;
+    int dev = 0;
+    APDE_CUDA(cudaGetDevice(&dev));
+    const bool use_cache = getenv("APDE_NO_PLAN_CACHE") == nullptr;
+    if (use_cache && g_cached_plan && g_cached_plan->device == dev && memcmp(&g_cached_plan->d, &d, sizeof(d)) == 0) {
+        p = g_cached_plan;
+        g_cached_plan = nullptr;
+        apply_env_knobs(p);
+    } else {
+        release_cached_plan();
+        APDE_TRY(plan_create(&p, &d));
+    }
+    struct Guard {
+        apde_plan *p;
+        bool keep;
+        ~Guard() {
+            if (keep) g_cached_plan = p;
+            else delete p;
+        }
+    } guard{p, use_cache};
+    p->omega = 1.0;
+    p->kcl = false;
+    p->stop_flag = nullptr;
+    if (p->variant != 1) {
+        set_error("solve_redblack_window: needs the streaming kernel family (APDE_RB_VARIANT unset or v1)");
+        return APDE_EINVAL;
+    }
+    float ms = 0.f;
+    APDE_TRY(elem == 8 ? solve_streamed_t<double>(p, grid, nh, nv, src, n_sweeps, band, rbh, &ms, win_lo, win_hi)
+                       : solve_streamed_t<float>(p, grid, nh, nv, src, n_sweeps, band, rbh, &ms, win_lo, win_hi));
+    APDE_TRY(plan_read_residuals(p, 0, n_sweeps, hist, 0));
+    if (ksec) *ksec = ms * 1e-3;
     return APDE_OK;
 }
 

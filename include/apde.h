@@ -89,6 +89,17 @@ int apde_solve_redblack_f32(double *grid, const double *noise_h, const double *n
                             double *residual_history, int64_t *iterations_run,
                             double *kernel_seconds);
 
+/* Fixed-sweep solve of a rows x cols array with a RESULT WINDOW: exactly n_sweeps sweeps (rows 0 and rows-1 and both
+ * edge columns are fixed, as always), streamed like the calls above; residual_history[k] is the maximum change of sweep k
+ * over the rows [win_lo, win_hi) only, and only those rows of `grid` are written back.  This is the building block of
+ * communication-avoiding row strips: information moves 2 rows per sweep, so a strip extended by G >= 2*n_sweeps rows on
+ * each interior side (an even number, to keep the red-black colouring) reproduces, inside its window, the sweeps of the
+ * whole grid bit for bit -- no halo exchange; the ranks only max-combine their residual histories.  Needs
+ * rows >= 2 bands (APDE_STREAM_BAND, default 1536) and the default kernel family. */
+int apde_solve_redblack_window(int dtype_bytes, double *grid, const double *noise_h, const double *noise_v,
+                               const double *source, int64_t rows, int64_t cols, int64_t n_sweeps, int temporal_depth,
+                               int64_t win_lo, int64_t win_hi, double *residual_history, double *kernel_seconds);
+
 /* The same one-shot solve spread over up to n_gpus devices of this box from ONE process: row strips,
  * halo rows pushed to the neighbours with CUDA peer copies over NVLink once per fused pass, per-sweep
  * residuals max-combined on the host.  dtype_bytes 8 = fp64, 4 = fp32.  Result is bitwise equal to

@@ -447,3 +447,38 @@ def test_streamed_solve_vs_oracle_and_tolerance_runs_stay_unstreamed(monkeypatch
     g2 = g0.copy()
     hist2, n2, _ = _backend.solve("redblack", g2, nh, nv, s, 1e-3, 4000, check_every=8, temporal_depth=4)
     assert n == n2 < 4000 and g.tobytes() == g2.tobytes() and hist.tobytes() == hist2.tobytes()
+
+
+@pytest.mark.parametrize("mode,sigma,src", [("redblack", 0.01, True), ("redblack", 0.0, True), ("redblack32", 0.01, False)])
+@pytest.mark.parametrize("k,depth,band,rbh", [(20, 4, 64, 16), (33, 3, 128, 32)])
+def test_windowed_solves_of_overlapping_strips_equal_the_whole_grid(mode, sigma, src, k, depth, band, rbh, monkeypatch, rb_variant):
+    """Communication-avoiding strips (apde_solve_redblack_window): each strip, extended by G = 2*k rows on its interior
+    side(s), is relaxed k sweeps on its own with no halo exchange; inside its window it reproduces the whole grid's
+    sweeps bit for bit, and the maximum of the strips' residual histories is the whole grid's."""
+    if rb_variant != "v1":
+        pytest.skip("the streamed schedule drives the register-window kernel family")
+    monkeypatch.setenv("APDE_STREAMED", "1")
+    monkeypatch.setenv("APDE_STREAM_BAND", str(band))
+    monkeypatch.setenv("APDE_STREAM_RBH", str(rbh))
+    rows, cols = 1300, 210
+    g0, nh, nv, s = random_problem(rows, cols, sigma, seed=k, with_source=src)
+    ref = g0.copy()
+    ref_hist, n, _ = _backend.solve(mode, ref, nh, nv, s, 0.0, k, temporal_depth=depth)
+    G = 2 * k
+    cuts = [0, 430, 880, rows]  # strip starts are even, like G: the colouring of a strip is the whole grid's
+    out = g0.copy()
+    hist = np.zeros(k)
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        lo, hi = max(0, a - G), min(rows, b + G)
+        sub = g0[lo:hi].copy()  # (a row slice is already contiguous: ascontiguousarray would alias g0)
+        sub0 = sub.copy()
+        sh, _ = _backend.solve_window(mode, sub, None if nh is None else np.ascontiguousarray(nh[lo:hi]),
+                                      None if nv is None else np.ascontiguousarray(nv[lo:hi - 1]),
+                                      None if s is None else np.ascontiguousarray(s[lo:hi]), k, a - lo, b - lo,
+                                      temporal_depth=depth)
+        assert sub[:a - lo].tobytes() == sub0[:a - lo].tobytes() and sub[b - lo:].tobytes() == sub0[b - lo:].tobytes()
+        out[a:b] = sub[a - lo:b - lo]
+        hist = np.maximum(hist, sh)
+    bad = np.nonzero(np.any(out != ref, axis=1))[0]
+    assert bad.size == 0, f"rows differing: {bad.size} between {bad.min()} and {bad.max()}: {bad[:12]}"
+    assert hist.tobytes() == ref_hist.tobytes()
