@@ -484,6 +484,12 @@ static int upload_t(apde_plan *p, int64_t win_lo, int64_t win_hi, const double *
         }
     }
     APDE_CUDA(cudaGetLastError());
+    // The colour-split operand planes are rebuilt HERE, behind the packs on the same stream -- not lazily by the first
+    // plan_run: in a multi-GPU pass that first call is phase 1 on the side stream, and the phase-2 launch on the main
+    // stream would read planes the split kernel is still writing (found in round 2's last session: the halo-exchange
+    // end-to-end path returned a few hundred rows with the previous source term after an upload; tests on small grids
+    // and the steady-state bench loop never saw it).
+    if (p->variant == 1) APDE_TRY(plan_refresh_split(p, 0));
     APDE_CUDA(cudaMemcpyAsync(p->u[1].p, p->u[0].p, p->plane_elems() * sizeof(T), cudaMemcpyDeviceToDevice, 0));
     // from pinned host memory the copies above are asynchronous; callers driving several devices
     // queue all uploads first and wait afterwards (every GPU has its own PCIe link)
@@ -522,10 +528,11 @@ template <typename T> static int fill_t(apde_plan *p, const apde_fill_desc *f) {
                                              p->GV<T>(), g, *f);
     APDE_CUDA(cudaGetLastError());
     APDE_CUDA(cudaMemcpy(p->u[1].p, p->u[0].p, p->plane_elems() * sizeof(T), cudaMemcpyDeviceToDevice));
+    p->split_dirty = true;
+    if (p->variant == 1) APDE_TRY(plan_refresh_split(p, 0));  // eagerly, like upload_t (see there)
     APDE_CUDA(cudaDeviceSynchronize());
     p->cur = 0;
     p->filled = true;
-    p->split_dirty = true;
     p->launches += 1;
     return APDE_OK;
 }
