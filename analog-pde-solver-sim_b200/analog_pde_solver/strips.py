@@ -29,6 +29,26 @@ def partition_rows(grows: int, world: int) -> List[Tuple[int, int]]:
     return out
 
 
+def overlapped_strip(begin: int, end: int, grows: int, n_sweeps: int) -> Tuple[int, int, int, int]:
+    """Communication-avoiding strip for a FIXED number of sweeps: the rows [lo, hi) a rank relaxes on its own and the
+    window [win_lo, win_hi) inside them (local indices) that reproduces the whole grid's sweeps bit for bit.
+
+    A red-black sweep moves information 2 rows, so after n_sweeps sweeps only rows within 2*n_sweeps - 1 of the artificial
+    (frozen) first / last row of the extended strip differ from the global solution.  The extension G is the smallest even
+    number >= 2*n_sweeps (even: the strip's own colouring (i + j) % 2 must be the grid's), clipped at the grid's real
+    boundary.  Feed `lo:hi` of the host arrays to `_backend.solve_window(..., win_lo, win_hi)` and max-combine the residual
+    histories of the ranks (include/apde.h: apde_solve_redblack_window)."""
+    if not (0 <= begin < end <= grows) or n_sweeps < 0:
+        raise ValueError("overlapped_strip: need 0 <= begin < end <= grows and n_sweeps >= 0")
+    g = 2 * n_sweeps
+    g += g % 2
+    lo = max(begin - g, 0)
+    if lo % 2:  # keep the colouring: an odd start moves one more row out (or in, at the boundary it is row 0 anyway)
+        lo -= 1
+    hi = min(end + g, grows)
+    return lo, hi, begin - lo, end - lo
+
+
 def sweep_groups(n_sweeps: int, depth: int) -> List[int]:
     """Split n_sweeps into groups of at most `depth` sweeps (one halo exchange per group)."""
     full, rest = divmod(n_sweeps, depth)

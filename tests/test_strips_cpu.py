@@ -128,3 +128,28 @@ def test_partition_and_groups():
     assert parts[0][0] == 0 and parts[-1][1] == 65536 and all(b - a == 8192 for a, b in parts)
     assert sweep_groups(32, 3) == [3] * 10 + [2]
     assert sweep_groups(4, 4) == [4] and sweep_groups(0, 4) == []
+
+
+def test_overlapped_strips_reproduce_the_whole_grid_without_halo_exchange():
+    """The dependence-cone statement behind apde_solve_redblack_window, on the CPU oracle: every strip, extended by
+    2*K ghost rows per interior side and relaxed K sweeps ON ITS OWN (first / last row frozen), equals the whole grid's
+    result inside its window bit for bit; the maximum of the strips' windowed residuals is the whole grid's residual."""
+    import oracle
+    from helpers import random_problem
+    from analog_pde_solver.strips import overlapped_strip, partition_rows
+    rows, cols, k = 181, 37, 9
+    g0, nh, nv, s = random_problem(rows, cols, 0.02, seed=4, with_source=True)
+    ref, ref_hist, _ = oracle.red_black(g0, nh, nv, s, k)
+    out = g0.copy()
+    for world in (2, 3, 5):
+        for begin, end in partition_rows(rows, world):
+            lo, hi, wl, wh = overlapped_strip(begin, end, rows, k)
+            assert lo % 2 == 0 and (lo == 0 or begin - lo >= 2 * k) and (hi == rows or hi - end >= 2 * k)
+            sub, _, _ = oracle.red_black(g0[lo:hi].copy(), nh[lo:hi].copy(), nv[lo:hi - 1].copy(), s[lo:hi].copy(), k)
+            out[begin:end] = sub[wl:wh]
+        assert out.tobytes() == ref.tobytes(), world
+    # one ghost row too few is not enough: the cone is exactly 2K - 1 rows deep
+    begin, end = partition_rows(rows, 2)[1]
+    lo = begin - (2 * k - 2)
+    sub, _, _ = oracle.red_black(g0[lo:].copy(), nh[lo:].copy(), nv[lo:].copy(), s[lo:].copy(), k)
+    assert sub[begin - lo:].tobytes() != ref[begin:].tobytes()
