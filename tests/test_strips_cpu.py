@@ -153,3 +153,27 @@ def test_overlapped_strips_reproduce_the_whole_grid_without_halo_exchange():
     lo = begin - (2 * k - 2)
     sub, _, _ = oracle.red_black(g0[lo:].copy(), nh[lo:].copy(), nv[lo:].copy(), s[lo:].copy(), k)
     assert sub[begin - lo:].tobytes() != ref[begin:].tobytes()
+
+
+def test_streamed_schedule_model_has_no_unordered_conflicts_and_reads_the_right_pass():
+    """tools/stream_schedule_sim.py: the band edges / chunks / lanes / events of the streamed one-shot solve, restated on the
+    CPU.  For random shapes every pair of operations the streams leave unordered touches disjoint rows, and every pass
+    reads exactly the previous pass on band + halo; dropping the cross-lane event, shifting the bands by less than the
+    halo, or starting a band one upload chunk early is caught."""
+    import importlib.util, os, random
+    spec = importlib.util.spec_from_file_location("stream_schedule_sim", os.path.join(os.path.dirname(__file__), "..", "tools", "stream_schedule_sim.py"))
+    sim = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sim)
+    rng = random.Random(7)
+    for _ in range(40):
+        td = rng.choice([1, 2, 3, 4])
+        B = rng.choice([32, 64, 96, 128, 256]) 
+        if B < 8 * td:
+            continue
+        rows = rng.randint(2 * B, 12 * B)
+        k = rng.randint(1, 90)
+        sim.check(rows, B, td, k, lanes=rng.choice([1, 2]), seed=rng.randint(0, 99))
+    sim.check(16384, 1536, 4, 256, lanes=2)  # the benchmark shape
+    for mutate in ("no_lane_event", "short_shift", "early_band"):
+        with pytest.raises(AssertionError):
+            sim.check(900, 64, 4, 40, lanes=2, mutate=mutate)
