@@ -177,3 +177,40 @@ def test_streamed_schedule_model_has_no_unordered_conflicts_and_reads_the_right_
     for mutate in ("no_lane_event", "short_shift", "early_band"):
         with pytest.raises(AssertionError):
             sim.check(900, 64, 4, 40, lanes=2, mutate=mutate)
+
+
+def _ca_worker(rank, world, port, rows, cols, k, out):
+    """One rank of the communication-avoiding driver (what bench.py does at N > 1 for its end-to-end figure): relax the
+    extended strip on its own -- here with the oracle -- take the residual maxima over the owned rows only, MAX all-reduce."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from analog_pde_solver.strips import overlapped_strip
+        g0, nh, nv, src = random_problem(rows, cols, 0.01, seed=11)
+        begin, end = partition_rows(rows, world)[rank]
+        lo, hi, wl, wh = overlapped_strip(begin, end, rows, k)
+        u = g0[lo:hi].copy()
+        hist = np.zeros(k)
+        for s in range(k):  # sweep by sweep, to take the windowed residual like apde_solve_redblack_window
+            before = u
+            u, _, _ = oracle.red_black(u, nh[lo:hi].copy(), nv[lo:hi - 1].copy(), src[lo:hi].copy(), 1)
+            hist[s] = np.abs(u[wl:wh] - before[wl:wh]).max()
+        t = torch.from_numpy(hist)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ref, ref_hist, _ = oracle.red_black(g0, nh, nv, src, k)
+        out[rank] = (u[wl:wh].tobytes() == ref[begin:end].tobytes(), t.numpy().tobytes() == ref_hist.tobytes(), hi - lo)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,rows,cols,k", [(2, 90, 21, 7), (3, 151, 18, 6)])
+def test_communication_avoiding_strips_gloo(world, rows, cols, k):
+    mgr = mp.get_context("spawn").Manager()
+    out = mgr.dict()
+    mp.spawn(_ca_worker, args=(world, _free_port(), rows, cols, k, out), nprocs=world, join=True)
+    assert len(out) == world
+    for rank in range(world):
+        ok_grid, ok_hist, sub_rows = out[rank]
+        assert ok_grid, f"rank {rank}: window rows differ from the whole-grid result"
+        assert ok_hist, f"rank {rank}: max-combined windowed residuals differ from the whole grid's"
