@@ -1192,7 +1192,10 @@ int solve_redblack(int elem, double *grid, const double *nh, const double *nv, c
         if (const char *v = getenv("APDE_STREAM_RBH")) rbh = std::max<int64_t>(8, atoll(v));
         const char *sw = getenv("APDE_STREAMED");  // "0": never, "1": whenever valid (tests), unset: large grids
         const bool valid = !(tol > 0.0) && omega == 1.0 && !kcl && p->variant == 1 && rows >= 2 * band && band >= 4 * 2 * (int64_t)temporal_depth;
-        const bool want = sw ? atoi(sw) != 0 : rows * cols >= (int64_t)1 << 24;
+        // by default only where it was measured to pay: a band launch is (rows per band / row block) x (column strips) work
+        // items, one full wave of the resident warps at >= ~12k columns; narrower grids would run their band launches
+        // half empty and keep the plain schedule
+        const bool want = sw ? atoi(sw) != 0 : (rows * cols >= (int64_t)1 << 24 && cols >= 12288);
         if (valid && want) {
             float ms = 0.f;
             APDE_TRY(elem == 8 ? solve_streamed_t<double>(p, grid, nh, nv, src, max_iter, band, rbh, &ms)

@@ -71,7 +71,7 @@ int apde_solve_exact_f64_path(double *grid, const double *noise_h, const double 
  *   _f64: fp64 arithmetic;  _f32: fp32 arithmetic (host arrays stay float64, converted on device).
  * check_every <= 0 => 32; temporal_depth <= 0 => library default (4); values above the
  * kernel family's maximum (4; 6 for APDE_RB_VARIANT=v2) are clamped.
- * A call that cannot stop early (tol <= 0, i.e. exactly max_iter sweeps) on a grid of >= 2^24 nodes is STREAMED:
+ * A call that cannot stop early (tol <= 0, i.e. exactly max_iter sweeps) on a grid of >= 2^24 nodes and >= 12288 columns is STREAMED:
  * the host arrays go up in row chunks, the fused passes follow the upload front band by band (parallelogram tiling:
  * the bands of pass p are shifted up by (p-1)*2*temporal_depth rows) and finished bands come back while later ones
  * are still relaxed -- same grid and residual history bit for bit, about half the wall time from pinned host memory.
