@@ -787,7 +787,7 @@ __global__ void __launch_bounds__(1024, 1) exact_ring_smem_kernel(K2Params p) {
 }
 
 // ------------------------------------------------------------------------------------------
-// K2c: row bands, every thread walks along ONE grid row (round 2; the default for large grids).
+// K2c: row bands, every thread walks along ONE grid row (round 2; measured slower than K2, opt-in: APDE_RING_KERNEL=band).
 //
 // The interior rows are cut into bands of NT rows; a CTA owns (sweep slot, band) and thread r of it
 // owns row i = 1 + band*NT + r for the whole launch.  At CTA step S thread r handles column
@@ -1236,7 +1236,7 @@ static int ring_configure(bool noise, bool src, int64_t rows, int64_t cols, int6
     const bool can4 = noise && smem4 + 1024 <= (size_t)prop.sharedMemPerBlockOptin;
     bool want4 = K2D_DEFAULT;
     if (force) want4 = !strcmp(force, "k2d");
-    // K2c (row bands): the default wherever its ring of sweep slots can be made short enough for the width
+    // K2c (row bands): possible wherever its ring of sweep slots can be made short enough for the width
     // (slots * (3*kb + 4) <= cols, see the kernel) -- i.e. everything but very narrow grids
     int band_kb = 4;
     if (const char *v = getenv("APDE_BAND_KB")) band_kb = std::min(64, std::max(1, atoi(v)));
