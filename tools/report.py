@@ -74,10 +74,13 @@ def main():
         for b in scal:
             n, e = b["n_gpus"], (b.get("e2e") or {}).get("value")
             par = (b.get("parity") or {}).get("multi_gpu_bitwise")
+            ca = (b.get("e2e") or {}).get("matches_halo_exchange_path")
             rows.append([n, fmt(b["value"]), fmt(b["value"] / (n * base), "{:.3f}"), fmt(e),
-                         fmt(None if not (e and base_e) else e / (n * base_e), "{:.3f}"), "-" if par is None else str(par)])
+                         fmt(None if not (e and base_e) else e / (n * base_e), "{:.3f}"), "-" if par is None else str(par),
+                         "-" if ca is None else str(ca)])
         print("\n## Weak scaling (efficiency = value(N) / (N * value(1)))\n")
-        print(table(rows, ["GPUs", "GLUP/s", "efficiency", "e2e GLUP/s", "e2e efficiency", "bitwise == 1 GPU"]))
+        print(table(rows, ["GPUs", "GLUP/s", "efficiency", "e2e GLUP/s", "e2e efficiency", "bitwise == 1 GPU",
+                           "e2e: overlapped strips == halo exchange"]))
     var = [(b.get("n_gpus"), v) for b in ours for v in (b.get("variants") or [])]
     if var:
         rows = []
