@@ -145,6 +145,16 @@ def test_bad_arguments_are_rejected_before_any_device_work():
         _backend.solve("exact", g, np.ones((4, 4)), None, None, 1e-6, 10)
     with pytest.raises(ValueError):
         _backend.solve("nonsense", g, None, None, None, 1e-6, 10)
+    # the windowed fixed-sweep solve: wrong mode / shapes in Python, too few rows or a bad window in the library -- all before
+    # any device work (this container has no GPU)
+    with pytest.raises(ValueError):
+        _backend.solve_window("exact", np.zeros((4000, 64)), None, None, None, 4, 0, 100)
+    with pytest.raises(ValueError):
+        _backend.solve_window("redblack", np.zeros((4000, 64)), np.ones((4000, 64)), None, None, 4, 0, 100)
+    for args in ((np.zeros((100, 64)), 4, 0, 50), (np.zeros((4000, 64)), 4, 200, 100), (np.zeros((4000, 64)), 4, 0, 4001)):
+        with pytest.raises(_backend.ApdeError) as e:
+            _backend.solve_window("redblack", args[0], None, None, None, *args[1:])
+        assert e.value.code == -1
 
 
 def test_degenerate_grid_raises_like_the_reference():
